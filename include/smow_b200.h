@@ -1,0 +1,140 @@
+/*
+ * smow_b200.h — C ABI of libsmow_b200.so (hand-written sm_100a CUDA kernels for
+ * SMOW-Net's flow-guided bi-temporal alignment / fusion hot path).
+ *
+ * The reference has NO native seam for this path: it is Python calling ATen
+ * (F.grid_sample / F.interpolate / torch.cat).  Each entry point below states
+ * which reference lines it replaces (paths relative to the reference tree).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the
+ *     current CUDA device of the calling thread; the caller owns every buffer;
+ *   - nothing is allocated, nothing synchronises; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return 0 on success, a negative SMOW_E* code for an argument error and a
+ *     positive value = cudaError_t for a launch failure.  A human-readable
+ *     message for the last failure of the calling thread: smow_last_error();
+ *   - no mutable global state except the launch counter and the tuning knobs,
+ *     so calls are re-entrant from the forward thread and the autograd thread.
+ *
+ * Tensor vocabulary (the reference's own):
+ *   frames   T1, T2   the two acquisition dates; a "pair" is one (T1,T2) sample
+ *   x        bi-temporal feature stack  (B, C, 2, H, W)
+ *   flow     predicted optical flow     (B, 2, 2, H, W)  = (b, {dx,dy}, frame, h, w), fp32
+ *   out      temporal stack             (B, C, 4, H, W)  = [T1, warp(T1), warp(T2), T2]
+ *   xs, ys   fp32 base-grid tables torch.linspace(-1,1,W) / (-1,1,H), built by the host
+ *            exactly like models/SMOW_Net.py:617-618 so coordinates match bit-for-bit
+ *
+ * dtype : SMOW_F32 (0) or SMOW_BF16 (1) for feature tensors; flow, xs, ys and
+ *         grad_flow are always fp32; all arithmetic is fp32.
+ * layout: SMOW_NCDHW (0): features are contiguous (B,C,T,H,W) — what cuDNN hands
+ *         the reference; SMOW_NDHWC (1): channels_last_3d, memory order
+ *         (B,T,H,W,C).  flow is always contiguous (B,2,2,H,W).
+ */
+#ifndef SMOW_B200_H
+#define SMOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMOW_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SMOW_API __attribute__((visibility("default")))
+#else
+#define SMOW_API
+#endif
+
+enum { SMOW_F32 = 0, SMOW_BF16 = 1 };
+enum { SMOW_NCDHW = 0, SMOW_NDHWC = 1 };
+
+enum {
+  SMOW_OK = 0,
+  SMOW_EINVAL = -1,   /* bad shape / null pointer                 */
+  SMOW_EALIGN = -2,   /* pointer or row pitch not 16-byte aligned  */
+  SMOW_EDTYPE = -3,   /* unsupported dtype / layout combination    */
+  SMOW_ERANGE = -4    /* tensor too large for 32-bit tile indexing */
+};
+
+SMOW_API int         smow_abi_version(void);
+SMOW_API const char* smow_last_error(void);
+/* Number of kernels this library has launched in this process (all threads). */
+SMOW_API uint64_t    smow_launch_count(void);
+/* Tuning knobs (ints), e.g. "warp_fwd_variant", "warp_bwd_variant".  Returns 0
+ * or SMOW_EINVAL for an unknown key.  smow_get_option returns the value or -1. */
+SMOW_API int         smow_set_option(const char* key, int value);
+SMOW_API int         smow_get_option(const char* key);
+
+/* ---- A1: OFW.flow_warp forward ------------------------------------------------
+ * Replaces models/SMOW_Net.py:612-638 (= models/SMOW_Net_LW.py:454-480): base grid
+ * + flow/[W,H], clamp(-1,1), per-frame grid_sample(bilinear, border,
+ * align_corners=True) (ATen GridSampler.cuh:21-31,53-57), and the time-axis
+ * concat [T1, warp(T1), warp(T2), T2] — one launch, warped frames never
+ * round-trip HBM.
+ *   x    (B,C,2,H,W)   out (B,C,4,H,W)                                            */
+SMOW_API int smow_warp_stack_fwd(const void* x, const float* flow,
+                        const float* xs, const float* ys, void* out,
+                        int B, int C, int H, int W,
+                        int dtype, int layout, void* stream);
+
+/* Same, with the two frames given as separate (B,C,H,W) tensors (the Siamese
+ * backbone outputs of models/SMOW_Net_LW.py:35-40, row A5): the unsqueeze+cat
+ * that builds the stack is skipped.                                              */
+SMOW_API int smow_warp_pair_fwd(const void* x_t1, const void* x_t2, const float* flow,
+                       const float* xs, const float* ys, void* out,
+                       int B, int C, int H, int W,
+                       int dtype, int layout, void* stream);
+
+/* ---- A1: backward of the same graph --------------------------------------------
+ * Replaces the autograd chain CatBackward → GridSampler2DBackward (ATen
+ * GridSampler.cuh:37-50,62-80) → ClampBackward → DivBackward → Select/Slice
+ * backward:
+ *   gx[:,:,0] = gout[:,:,0] + scatter(gout[:,:,1]);  gx[:,:,1] = gout[:,:,3] + scatter(gout[:,:,2])
+ *   gflow     = d(out)/d(flow) with the clamp mask (inclusive at ±1) and the
+ *               border-clip mask.  gx needs no zero-fill by the caller.
+ *   gout (B,C,4,H,W)  x (B,C,2,H,W)  gx (B,C,2,H,W)  gflow (B,2,2,H,W) fp32      */
+SMOW_API int smow_warp_stack_bwd(const void* gout, const void* x, const float* flow,
+                        const float* xs, const float* ys,
+                        void* gx, float* gflow,
+                        int B, int C, int H, int W,
+                        int dtype, int layout, void* stream);
+
+SMOW_API int smow_warp_pair_bwd(const void* gout, const void* x_t1, const void* x_t2,
+                       const float* flow, const float* xs, const float* ys,
+                       void* gx_t1, void* gx_t2, float* gflow,
+                       int B, int C, int H, int W,
+                       int dtype, int layout, void* stream);
+
+/* ---- A3+A4: temporal 2→4 lerp written straight into the decoder concat ----------
+ * Replaces F.interpolate(xk, size=(4,h,w), 'trilinear', align_corners=True)
+ * (models/SMOW_Net.py:64-73, models/SMOW_Net_LW.py:62-71) followed by
+ * torch.cat([c3dtK, xK], dim=1) (models/SMOW_Net.py:78,82,86,90,94):
+ *   cat[:, :Cd]        = dec                      (B,Cd,4,h,w)   (skipped if dec == NULL)
+ *   cat[:, Cd:Cd+Cs]   = [T1, (1-l)T1+l*T2, (1-m)T1+m*T2, T2]    (skipped if skip == NULL)
+ * with l = fp32(1/3), m = 2*l as ATen's upsample_trilinear3d computes them.
+ * skip is (B,Cs,2,h,w) (or two (B,Cs,h,w) tensors for the _pair variant).
+ * hw = h*w.  Cd may be 0 (stand-alone temporal upsample).                         */
+SMOW_API int smow_tlerp_cat_fwd(const void* dec, const void* skip, void* cat,
+                       int B, int Cd, int Cs, int64_t hw,
+                       int dtype, int layout, void* stream);
+SMOW_API int smow_tlerp_pair_cat_fwd(const void* dec, const void* skip_t1, const void* skip_t2,
+                            void* cat, int B, int Cd, int Cs, int64_t hw,
+                            int dtype, int layout, void* stream);
+
+/* Backward: gskip[:,:,0] = g0 + (1-l)g1 + (1-m)g2 ; gskip[:,:,1] = l*g1 + m*g2 + g3
+ * where g = gcat[:, Cd:Cd+Cs].  The dec half of gcat is consumed in place by the
+ * caller as a strided view (what torch.cat's backward does), so it is not copied. */
+SMOW_API int smow_tlerp_cat_bwd(const void* gcat, void* gskip,
+                       int B, int Cd, int Cs, int64_t hw,
+                       int dtype, int layout, void* stream);
+SMOW_API int smow_tlerp_pair_cat_bwd(const void* gcat, void* gskip_t1, void* gskip_t2,
+                            int B, int Cd, int Cs, int64_t hw,
+                            int dtype, int layout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMOW_B200_H */

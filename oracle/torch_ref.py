@@ -1,0 +1,62 @@
+"""PyTorch restatement of the reference's hot path — TEST INFRASTRUCTURE ONLY.
+
+These functions issue the same ATen calls, in the same order, as the reference code they
+cite, so on any device they reproduce "the reference's own PyTorch path" (north_star) even
+where /root/reference itself is not present (the GPU box).  oracle/make_golden.py asserts
+bit-equality with the real reference in the build container.
+
+The product package never imports this file.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def ref_flow_warp(input, flow):
+    """OFW.flow_warp — reference models/SMOW_Net.py:612-638 (= models/SMOW_Net_LW.py:454-480)."""
+    B, C, T, H, W = input.shape
+    # :617-621  CPU fp32 linspace base grid, shipped to the device each call
+    ys = torch.linspace(-1.0, 1.0, H).view(-1, 1).expand(H, W)
+    xs = torch.linspace(-1.0, 1.0, W).view(1, -1).expand(H, W)
+    grid = torch.stack((xs, ys), 2).unsqueeze(0).expand(B, H, W, 2).type_as(input).to(input.device)
+    norm = torch.tensor([[[[W, H]]]]).type_as(input).to(input.device)       # :627
+    frames = []
+    for t in range(T):                                                       # :623-632
+        field = flow[:, :, t].permute(0, 2, 3, 1) / norm
+        warped = F.grid_sample(input[:, :, t], (grid + field).clamp(-1, 1), mode="bilinear",
+                               padding_mode="border", align_corners=True)
+        frames.append(warped.unsqueeze(2))
+    return torch.cat([input[:, :, 0:1]] + frames + [input[:, :, 1:2]], dim=2)   # :634-636
+
+
+def ref_tlerp(skip):
+    """Temporal 2 -> 4 upsample — reference models/SMOW_Net.py:64-73."""
+    b, c, t, h, w = skip.shape
+    return F.interpolate(skip, size=(4, h, w), mode="trilinear", align_corners=True)
+
+
+def ref_tlerp_cat(dec, skip):
+    """Upsample + decoder skip concat — reference models/SMOW_Net.py:64-73 and :78,82,86,90,94."""
+    up = ref_tlerp(skip)
+    return up if dec is None else torch.cat([dec, up], dim=1)
+
+
+def ref_pair_stack(x_t1, x_t2):
+    """Bi-temporal stacking — reference models/SMOW_Net_LW.py:38-40."""
+    return torch.cat([x_t1.unsqueeze(2), x_t2.unsqueeze(2)], 2)
+
+
+def warp_with_grads(x, flow, gout):
+    """(out, grad_x, grad_flow) of ref_flow_warp by autograd, detached."""
+    x = x.detach().clone().requires_grad_(True)
+    flow = flow.detach().clone().requires_grad_(True)
+    out = ref_flow_warp(x, flow)
+    out.backward(gout)
+    return out.detach(), x.grad.detach(), flow.grad.detach()
+
+
+def tlerp_cat_with_grads(dec, skip, gcat):
+    skip = skip.detach().clone().requires_grad_(True)
+    d = None if dec is None else dec.detach().clone().requires_grad_(True)
+    cat = ref_tlerp_cat(d, skip)
+    cat.backward(gcat)
+    return cat.detach(), (None if d is None else d.grad.detach()), skip.grad.detach()

@@ -1,0 +1,233 @@
+// A3 + A4: temporal 2 -> 4 linear upsample of an encoder skip, written straight into
+// the decoder's channel concat, and its backward (sm_100a, pure HBM streaming).
+//
+// Reference (models/SMOW_Net.py:64-73,78-94): F.interpolate(x, size=(4,h,w), 'trilinear',
+// align_corners=True) then torch.cat([dec, x_up], dim=1).  With unchanged h,w the 8-tap
+// trilinear kernel degenerates to out[t] = (1-l_t) T1 + l_t T2, l = {0, 1/3, 2/3, 1} in
+// fp32 (ATen UpSampleTrilinear3d: rdepth = (2-1)/(4-1); frames 0 and 3 are exact copies).
+#include "common.cuh"
+
+namespace smow {
+
+template <typename T> struct Vec;   // 16-byte vector of T
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  float v[4];
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __nv_bfloat16 v[8];
+};
+
+template <typename T> __device__ __forceinline__ Vec<T> ldv(const T* p) {
+  Vec<T> r;
+  *reinterpret_cast<uint4*>(r.v) = __ldg(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+template <typename T> __device__ __forceinline__ Vec<T> ldv_stream(const T* p) {
+  Vec<T> r;
+  *reinterpret_cast<uint4*>(r.v) = __ldcs(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+template <typename T> __device__ __forceinline__ void stv(T* p, const Vec<T>& r) {
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(r.v);
+}
+
+struct LerpW { float a1, b1, a2, b2; };
+__device__ __forceinline__ LerpW lerp_weights() {
+  LerpW w;
+  w.b1 = SMOW_LAMBDA1; w.a1 = __fsub_rn(1.f, SMOW_LAMBDA1);
+  w.b2 = SMOW_LAMBDA2; w.a2 = __fsub_rn(1.f, SMOW_LAMBDA2);
+  return w;
+}
+
+// One launch: blocks [0, lerp_blocks) lerp the skip into cat[:, Cd:], the rest copy dec
+// into cat[:, :Cd].  VEC = elements per thread-access (16 B vectors, or 1 for odd shapes).
+template <typename T, bool VECTOR>
+__global__ void __launch_bounds__(256)
+tlerp_cat_fwd_kernel(const T* __restrict__ dec, const T* __restrict__ s1, const T* __restrict__ s2,
+                     int64_t sB, int64_t sC, T* __restrict__ cat, int Cd, int Cs, int64_t hw,
+                     int64_t n_lerp, int64_t n_copy, int lerp_blocks) {
+  constexpr int V = VECTOR ? Vec<T>::N : 1;
+  const int Ct = Cd + Cs;
+  if ((int)blockIdx.x < lerp_blocks) {
+    const LerpW lw = lerp_weights();
+    const int64_t hwv = hw / V;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_lerp; i += (int64_t)lerp_blocks * 256) {
+      const int64_t bc = i / hwv, e = (i - bc * hwv) * V;
+      const int64_t b = bc / Cs, c = bc - b * Cs;
+      const T* p1 = s1 + b * sB + c * sC + e;
+      const T* p2 = s2 + b * sB + c * sC + e;
+      T* o = cat + ((b * Ct + Cd + c) * 4) * hw + e;
+      if constexpr (VECTOR) {
+        const Vec<T> a = ldv(p1), bb = ldv(p2);
+        Vec<T> m1, m2;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float fa = cvtf<T>(a.v[j]), fb = cvtf<T>(bb.v[j]);
+          m1.v[j] = fromf<T>(fmaf(lw.a1, fa, __fmul_rn(lw.b1, fb)));
+          m2.v[j] = fromf<T>(fmaf(lw.a2, fa, __fmul_rn(lw.b2, fb)));
+        }
+        stv(o, a); stv(o + hw, m1); stv(o + 2 * hw, m2); stv(o + 3 * hw, bb);
+      } else {
+        const float fa = ldf(p1), fb = ldf(p2);
+        o[0] = *p1;
+        o[hw] = fromf<T>(fmaf(lw.a1, fa, __fmul_rn(lw.b1, fb)));
+        o[2 * hw] = fromf<T>(fmaf(lw.a2, fa, __fmul_rn(lw.b2, fb)));
+        o[3 * hw] = *p2;
+      }
+    }
+  } else {
+    const int cb = (int)gridDim.x - lerp_blocks;
+    const int64_t per_b = (int64_t)Cd * 4 * hw / V;   // vectors of dec per pair
+    for (int64_t i = (int64_t)(blockIdx.x - lerp_blocks) * 256 + threadIdx.x; i < n_copy;
+         i += (int64_t)cb * 256) {
+      const int64_t b = i / per_b, r = (i - b * per_b) * V;
+      const T* src = dec + b * (int64_t)Cd * 4 * hw + r;
+      T* dst = cat + b * (int64_t)Ct * 4 * hw + r;
+      if constexpr (VECTOR) stv(dst, ldv_stream(src));
+      else *dst = *src;
+    }
+  }
+}
+
+template <typename T, bool VECTOR>
+__global__ void __launch_bounds__(256)
+tlerp_cat_bwd_kernel(const T* __restrict__ gcat, T* __restrict__ g1, T* __restrict__ g2, int64_t sB,
+                     int64_t sC, int Cd, int Cs, int64_t hw, int64_t n) {
+  constexpr int V = VECTOR ? Vec<T>::N : 1;
+  const int Ct = Cd + Cs;
+  const LerpW lw = lerp_weights();
+  const int64_t hwv = hw / V;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int64_t bc = i / hwv, e = (i - bc * hwv) * V;
+    const int64_t b = bc / Cs, c = bc - b * Cs;
+    const T* g = gcat + ((b * Ct + Cd + c) * 4) * hw + e;
+    T* o1 = g1 + b * sB + c * sC + e;
+    T* o2 = g2 + b * sB + c * sC + e;
+    if constexpr (VECTOR) {
+      const Vec<T> a = ldv_stream(g), m1 = ldv_stream(g + hw), m2 = ldv_stream(g + 2 * hw),
+                   d = ldv_stream(g + 3 * hw);
+      Vec<T> r1, r2;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float f0 = cvtf<T>(a.v[j]), f1 = cvtf<T>(m1.v[j]), f2 = cvtf<T>(m2.v[j]), f3 = cvtf<T>(d.v[j]);
+        r1.v[j] = fromf<T>(fmaf(lw.a2, f2, fmaf(lw.a1, f1, f0)));
+        r2.v[j] = fromf<T>(__fadd_rn(fmaf(lw.b2, f2, __fmul_rn(lw.b1, f1)), f3));
+      }
+      stv(o1, r1); stv(o2, r2);
+    } else {
+      const float f0 = cvtf<T>(g[0]), f1 = cvtf<T>(g[hw]), f2 = cvtf<T>(g[2 * hw]), f3 = cvtf<T>(g[3 * hw]);
+      *o1 = fromf<T>(fmaf(lw.a2, f2, fmaf(lw.a1, f1, f0)));
+      *o2 = fromf<T>(__fadd_rn(fmaf(lw.b2, f2, __fmul_rn(lw.b1, f1)), f3));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------
+// host dispatch
+// ------------------------------------------------------------------------------
+template <typename T>
+static int fwd_impl(const T* dec, const T* s1, const T* s2, int64_t sB, int64_t sC, T* cat, int B, int Cd,
+                    int Cs, int64_t hw, cudaStream_t st) {
+  constexpr int V = Vec<T>::N;
+  const bool do_lerp = s1 != nullptr, do_copy = dec != nullptr && Cd > 0;
+  if (!do_lerp && !do_copy) return 0;
+  bool vec = (hw % V == 0) && aligned16(cat);
+  if (do_lerp) vec = vec && aligned16(s1) && aligned16(s2) && (sB % V == 0) && (sC % V == 0);
+  if (do_copy) vec = vec && aligned16(dec);
+  const int v = vec ? V : 1;
+  const int64_t n_lerp = do_lerp ? (int64_t)B * Cs * (hw / v) : 0;
+  const int64_t n_copy = do_copy ? (int64_t)B * Cd * 4 * (hw / v) : 0;
+  const int cap = device_info().sms * 8;
+  int lb = (int)((n_lerp + 255) / 256 < cap ? (n_lerp + 255) / 256 : cap);
+  int cb = (int)((n_copy + 511) / 512 < cap ? (n_copy + 511) / 512 : cap);
+  if (vec)
+    tlerp_cat_fwd_kernel<T, true><<<lb + cb, 256, 0, st>>>(dec, s1, s2, sB, sC, cat, Cd, Cs, hw, n_lerp, n_copy, lb);
+  else
+    tlerp_cat_fwd_kernel<T, false><<<lb + cb, 256, 0, st>>>(dec, s1, s2, sB, sC, cat, Cd, Cs, hw, n_lerp, n_copy, lb);
+  count_launch();
+  return check_launch("tlerp_cat_fwd");
+}
+
+template <typename T>
+static int bwd_impl(const T* gcat, T* g1, T* g2, int64_t sB, int64_t sC, int B, int Cd, int Cs, int64_t hw,
+                    cudaStream_t st) {
+  constexpr int V = Vec<T>::N;
+  const bool vec = (hw % V == 0) && aligned16(gcat) && aligned16(g1) && aligned16(g2) && (sB % V == 0) &&
+                   (sC % V == 0);
+  const int v = vec ? V : 1;
+  const int64_t n = (int64_t)B * Cs * (hw / v);
+  const int cap = device_info().sms * 8;
+  const int nb = (int)((n + 255) / 256 < cap ? (n + 255) / 256 : cap);
+  if (vec) tlerp_cat_bwd_kernel<T, true><<<nb, 256, 0, st>>>(gcat, g1, g2, sB, sC, Cd, Cs, hw, n);
+  else tlerp_cat_bwd_kernel<T, false><<<nb, 256, 0, st>>>(gcat, g1, g2, sB, sC, Cd, Cs, hw, n);
+  count_launch();
+  return check_launch("tlerp_cat_bwd");
+}
+
+static int check_args(const void* cat, int B, int Cd, int Cs, int64_t hw, int dtype, int layout) {
+  if (!cat) return fail(SMOW_EINVAL, "null pointer argument");
+  if (B <= 0 || Cd < 0 || Cs <= 0 || hw <= 0) return fail(SMOW_EINVAL, "bad shape B=%d Cd=%d Cs=%d hw=%lld", B, Cd, Cs, (long long)hw);
+  if (dtype != SMOW_F32 && dtype != SMOW_BF16) return fail(SMOW_EDTYPE, "unsupported dtype %d", dtype);
+  if (layout != SMOW_NCDHW) return fail(SMOW_EDTYPE, "tlerp_cat: only the NCDHW layout is built");
+  return 0;
+}
+
+}  // namespace smow
+
+using namespace smow;
+
+extern "C" {
+
+int smow_tlerp_pair_cat_fwd(const void* dec, const void* skip_t1, const void* skip_t2, void* cat, int B, int Cd,
+                            int Cs, int64_t hw, int dtype, int layout, void* stream) {
+  if (int e = check_args(cat, B, Cd, Cs, hw, dtype, layout)) return e;
+  if ((skip_t1 == nullptr) != (skip_t2 == nullptr)) return fail(SMOW_EINVAL, "skip_t1/skip_t2 must both be set or both be NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMOW_F32)
+    return fwd_impl<float>((const float*)dec, (const float*)skip_t1, (const float*)skip_t2, Cs * hw, hw,
+                           (float*)cat, B, Cd, Cs, hw, st);
+  return fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dec, (const __nv_bfloat16*)skip_t1,
+                                 (const __nv_bfloat16*)skip_t2, Cs * hw, hw, (__nv_bfloat16*)cat, B, Cd, Cs, hw, st);
+}
+
+int smow_tlerp_cat_fwd(const void* dec, const void* skip, void* cat, int B, int Cd, int Cs, int64_t hw,
+                       int dtype, int layout, void* stream) {
+  if (int e = check_args(cat, B, Cd, Cs, hw, dtype, layout)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMOW_F32) {
+    const float* s = (const float*)skip;
+    return fwd_impl<float>((const float*)dec, s, s ? s + hw : nullptr, 2 * Cs * hw, 2 * hw, (float*)cat, B, Cd,
+                           Cs, hw, st);
+  }
+  const __nv_bfloat16* s = (const __nv_bfloat16*)skip;
+  return fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dec, s, s ? s + hw : nullptr, 2 * Cs * hw, 2 * hw,
+                                 (__nv_bfloat16*)cat, B, Cd, Cs, hw, st);
+}
+
+int smow_tlerp_pair_cat_bwd(const void* gcat, void* gskip_t1, void* gskip_t2, int B, int Cd, int Cs, int64_t hw,
+                            int dtype, int layout, void* stream) {
+  if (int e = check_args(gcat, B, Cd, Cs, hw, dtype, layout)) return e;
+  if (!gskip_t1 || !gskip_t2) return fail(SMOW_EINVAL, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMOW_F32)
+    return bwd_impl<float>((const float*)gcat, (float*)gskip_t1, (float*)gskip_t2, Cs * hw, hw, B, Cd, Cs, hw, st);
+  return bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)gcat, (__nv_bfloat16*)gskip_t1, (__nv_bfloat16*)gskip_t2,
+                                 Cs * hw, hw, B, Cd, Cs, hw, st);
+}
+
+int smow_tlerp_cat_bwd(const void* gcat, void* gskip, int B, int Cd, int Cs, int64_t hw, int dtype, int layout,
+                       void* stream) {
+  if (int e = check_args(gcat, B, Cd, Cs, hw, dtype, layout)) return e;
+  if (!gskip) return fail(SMOW_EINVAL, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMOW_F32) {
+    float* g = (float*)gskip;
+    return bwd_impl<float>((const float*)gcat, g, g + hw, 2 * Cs * hw, 2 * hw, B, Cd, Cs, hw, st);
+  }
+  __nv_bfloat16* g = (__nv_bfloat16*)gskip;
+  return bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)gcat, g, g + hw, 2 * Cs * hw, 2 * hw, B, Cd, Cs, hw, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,330 @@
+"""Autograd operators of the SMOW-Net alignment/fusion hot path (CUDA only).
+
+Python mirror of the reference's operator interface for this path:
+
+* ``flow_warp(input, flow, size)``     - ``OFW.flow_warp`` (reference models/SMOW_Net.py:612-638)
+* ``warp_pair(x_t1, x_t2, flow)``      - same, frames not yet stacked (models/SMOW_Net_LW.py:38-40,58)
+* ``tlerp_cat(dec, skip)``             - ``F.interpolate(skip, (4,h,w), 'trilinear', True)`` +
+  ``torch.cat([dec, skip_up], 1)``     (models/SMOW_Net.py:64-73,78-94)
+* ``tlerp(skip)`` / ``tlerp_pair_cat`` - stand-alone / un-stacked forms of the same
+
+Every operator calls libsmow_b200.so through the C ABI of include/smow_b200.h.  There is
+no CPU implementation and no PyTorch fallback: CPU tensors raise.
+"""
+import contextlib
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+# ----------------------------------------------------------------------------- helpers
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "smow_net_b200 operators run on CUDA tensors only (hand-written sm_100a kernels, "
+                "no CPU fallback); got a %s tensor" % t.device)
+
+
+def _dtype_code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError("smow_net_b200: unsupported dtype %s (fp32 and bf16 only)" % t.dtype)
+
+
+def _layout5(t):
+    """(tensor, layout code) with the tensor made dense in one of the two supported orders."""
+    if t.is_contiguous():
+        return t, _lib.NCDHW
+    if t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d):
+        return t, _lib.NDHWC
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return t, _lib.NDHWC
+    return t.contiguous(), _lib.NCDHW
+
+
+def _as_layout(t, layout):
+    if layout == _lib.NCDHW:
+        return t.contiguous()
+    fmt = torch.channels_last_3d if t.dim() == 5 else torch.channels_last
+    return t.contiguous(memory_format=fmt)
+
+
+def _empty(shape, like, layout):
+    fmt = torch.contiguous_format
+    if layout == _lib.NDHWC:
+        fmt = torch.channels_last_3d if len(shape) == 5 else torch.channels_last
+    return torch.empty(shape, dtype=like.dtype, device=like.device, memory_format=fmt)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_GRID_CACHE = {}
+
+
+def base_grid(n, device):
+    """fp32 table torch.linspace(-1, 1, n) built on the CPU exactly as the reference does
+    (models/SMOW_Net.py:617-618) and cached on the device, so the coordinate chain is
+    reproduced bit for bit without the reference's per-call host-to-device copy."""
+    key = (int(n), device.index if device.index is not None else torch.cuda.current_device())
+    t = _GRID_CACHE.get(key)
+    if t is None:
+        t = torch.linspace(-1.0, 1.0, int(n)).to(device)
+        _GRID_CACHE[key] = t
+    return t
+
+
+# ------------------------------------------------------------------- per-launch timing hook
+class KernelTimer:
+    """Collects CUDA-event timings of every C-ABI call made while active (bench.py roofline)."""
+
+    def __init__(self):
+        self.records = []  # (name, algorithmic_bytes, start_event, end_event)
+
+    def summary(self):
+        out = {}
+        for name, nbytes, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            s = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0})
+            s["calls"] += 1
+            s["ms"] += ms
+            s["bytes"] += nbytes
+        for s in out.values():
+            s["gbps"] = s["bytes"] / (s["ms"] * 1e-3) / 1e9 if s["ms"] > 0 else 0.0
+        return out
+
+
+_TIMER = None
+
+
+@contextlib.contextmanager
+def kernel_timer():
+    global _TIMER
+    prev, _TIMER = _TIMER, KernelTimer()
+    try:
+        yield _TIMER
+    finally:
+        _TIMER = prev
+
+
+def _call(name, nbytes, fn, *args):
+    if _TIMER is None:
+        _lib.check(fn(*args), name)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.check(fn(*args), name)
+    e1.record()
+    _TIMER.records.append((name, nbytes, e0, e1))
+
+
+# algorithmic bytes per launch; s = bytes per feature element, flow is fp32
+def warp_fwd_bytes(B, C, H, W, s):
+    return B * (6 * C * H * W * s + 16 * H * W)
+
+
+def warp_bwd_bytes(B, C, H, W, s):
+    return B * (8 * C * H * W * s + 32 * H * W)
+
+
+def tlerp_fwd_bytes(B, Cd, Cs, hw, s):
+    return B * (6 * Cs * hw * s + 8 * Cd * hw * s)
+
+
+def tlerp_bwd_bytes(B, Cs, hw, s):
+    return B * 6 * Cs * hw * s
+
+
+# ----------------------------------------------------------------------------- A1: warp + stack
+class _WarpStack(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flow):
+        _require_cuda(x, flow)
+        if x.dim() != 5 or x.shape[2] != 2:
+            raise RuntimeError("flow_warp: input must be (B,C,2,H,W), got %s" % (tuple(x.shape),))
+        B, C, _, H, W = x.shape
+        if tuple(flow.shape) != (B, 2, 2, H, W):
+            raise RuntimeError("flow_warp: flow must be (B,2,2,H,W)=%s, got %s" % ((B, 2, 2, H, W), tuple(flow.shape)))
+        x, layout = _layout5(x)
+        flow = flow.float().contiguous()
+        out = _empty((B, C, 4, H, W), x, layout)
+        xs, ys = base_grid(W, x.device), base_grid(H, x.device)
+        lib = _lib.load()
+        with torch.cuda.device_of(x):
+            _call("warp_stack_fwd", warp_fwd_bytes(B, C, H, W, x.element_size()), lib.smow_warp_stack_fwd,
+                  x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(), out.data_ptr(),
+                  B, C, H, W, _dtype_code(x), layout, _stream())
+        ctx.save_for_backward(x, flow)
+        ctx.layout = layout
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, flow = ctx.saved_tensors
+        B, C, _, H, W = x.shape
+        gout = _as_layout(gout, ctx.layout)
+        gx = _empty(tuple(x.shape), x, ctx.layout)
+        gflow = torch.empty_like(flow)
+        xs, ys = base_grid(W, x.device), base_grid(H, x.device)
+        lib = _lib.load()
+        with torch.cuda.device_of(x):
+            _call("warp_stack_bwd", warp_bwd_bytes(B, C, H, W, x.element_size()), lib.smow_warp_stack_bwd,
+                  gout.data_ptr(), x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),
+                  gx.data_ptr(), gflow.data_ptr(), B, C, H, W, _dtype_code(x), ctx.layout, _stream())
+        return gx, gflow
+
+
+class _WarpPair(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, flow):
+        _require_cuda(x1, x2, flow)
+        if x1.dim() != 4 or x1.shape != x2.shape or x1.dtype != x2.dtype:
+            raise RuntimeError("warp_pair: x_t1/x_t2 must be matching (B,C,H,W) tensors")
+        B, C, H, W = x1.shape
+        if tuple(flow.shape) != (B, 2, 2, H, W):
+            raise RuntimeError("warp_pair: flow must be (B,2,2,H,W)")
+        x1, layout = _layout5(x1)
+        x2 = _as_layout(x2, layout)
+        flow = flow.float().contiguous()
+        out = _empty((B, C, 4, H, W), x1, layout)
+        xs, ys = base_grid(W, x1.device), base_grid(H, x1.device)
+        lib = _lib.load()
+        with torch.cuda.device_of(x1):
+            _call("warp_stack_fwd", warp_fwd_bytes(B, C, H, W, x1.element_size()), lib.smow_warp_pair_fwd,
+                  x1.data_ptr(), x2.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(), out.data_ptr(),
+                  B, C, H, W, _dtype_code(x1), layout, _stream())
+        ctx.save_for_backward(x1, x2, flow)
+        ctx.layout = layout
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x1, x2, flow = ctx.saved_tensors
+        B, C, H, W = x1.shape
+        gout = _as_layout(gout, ctx.layout)
+        g1 = _empty(tuple(x1.shape), x1, ctx.layout)
+        g2 = _empty(tuple(x1.shape), x1, ctx.layout)
+        gflow = torch.empty_like(flow)
+        xs, ys = base_grid(W, x1.device), base_grid(H, x1.device)
+        lib = _lib.load()
+        with torch.cuda.device_of(x1):
+            _call("warp_stack_bwd", warp_bwd_bytes(B, C, H, W, x1.element_size()), lib.smow_warp_pair_bwd,
+                  gout.data_ptr(), x1.data_ptr(), x2.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),
+                  g1.data_ptr(), g2.data_ptr(), gflow.data_ptr(), B, C, H, W, _dtype_code(x1), ctx.layout,
+                  _stream())
+        return g1, g2, gflow
+
+
+def flow_warp(input, flow, size=None):
+    """Drop-in for ``OFW.flow_warp(input, flow, size)``: (B,C,2,H,W),(B,2,2,H,W) -> (B,C,4,H,W).
+
+    ``size`` is accepted for signature compatibility; like the reference it must equal the
+    spatial size of ``input`` (the reference's cat at :636 fails otherwise)."""
+    if size is not None and tuple(size) != tuple(input.shape[3:]):
+        raise RuntimeError("flow_warp: size %s must equal the input's spatial size %s"
+                           % (tuple(size), tuple(input.shape[3:])))
+    return _WarpStack.apply(input, flow)
+
+
+def warp_pair(x_t1, x_t2, flow):
+    """flow_warp on two un-stacked (B,C,H,W) frames -> (B,C,4,H,W)."""
+    return _WarpPair.apply(x_t1, x_t2, flow)
+
+
+# ----------------------------------------------------------------------------- A3+A4: tlerp + concat
+class _TLerpCat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dec, skip):
+        _require_cuda(dec, skip)
+        if skip.dim() != 5 or skip.shape[2] != 2:
+            raise RuntimeError("tlerp_cat: skip must be (B,Cs,2,h,w), got %s" % (tuple(skip.shape),))
+        B, Cs, _, h, w = skip.shape
+        Cd = 0
+        skip = skip.contiguous()
+        if dec is not None:
+            if dec.dim() != 5 or dec.shape[0] != B or dec.shape[2] != 4 or tuple(dec.shape[3:]) != (h, w):
+                raise RuntimeError("tlerp_cat: dec must be (B,Cd,4,h,w) matching skip, got %s" % (tuple(dec.shape),))
+            if dec.dtype != skip.dtype:
+                raise RuntimeError("tlerp_cat: dec and skip dtypes differ")
+            dec = dec.contiguous()
+            Cd = dec.shape[1]
+        cat = torch.empty((B, Cd + Cs, 4, h, w), dtype=skip.dtype, device=skip.device)
+        lib = _lib.load()
+        with torch.cuda.device_of(skip):
+            _call("tlerp_cat_fwd", tlerp_fwd_bytes(B, Cd, Cs, h * w, skip.element_size()), lib.smow_tlerp_cat_fwd,
+                  dec.data_ptr() if dec is not None else None, skip.data_ptr(), cat.data_ptr(),
+                  B, Cd, Cs, h * w, _dtype_code(skip), _lib.NCDHW, _stream())
+        ctx.dims = (B, Cd, Cs, h, w)
+        return cat
+
+    @staticmethod
+    def backward(ctx, gcat):
+        B, Cd, Cs, h, w = ctx.dims
+        gcat = gcat.contiguous()
+        gskip = torch.empty((B, Cs, 2, h, w), dtype=gcat.dtype, device=gcat.device)
+        lib = _lib.load()
+        with torch.cuda.device_of(gcat):
+            _call("tlerp_cat_bwd", tlerp_bwd_bytes(B, Cs, h * w, gcat.element_size()), lib.smow_tlerp_cat_bwd,
+                  gcat.data_ptr(), gskip.data_ptr(), B, Cd, Cs, h * w, _dtype_code(gcat), _lib.NCDHW, _stream())
+        gdec = gcat[:, :Cd] if Cd > 0 else None  # strided view, as torch.cat's backward returns
+        return gdec, gskip
+
+
+class _TLerpPairCat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dec, a, b):
+        _require_cuda(dec, a, b)
+        if a.dim() != 4 or a.shape != b.shape or a.dtype != b.dtype:
+            raise RuntimeError("tlerp_pair_cat: frames must be matching (B,Cs,h,w) tensors")
+        B, Cs, h, w = a.shape
+        a, b = a.contiguous(), b.contiguous()
+        Cd = 0
+        if dec is not None:
+            if dec.dim() != 5 or dec.shape[0] != B or dec.shape[2] != 4 or tuple(dec.shape[3:]) != (h, w):
+                raise RuntimeError("tlerp_pair_cat: dec must be (B,Cd,4,h,w) matching the frames")
+            dec = dec.contiguous()
+            Cd = dec.shape[1]
+        cat = torch.empty((B, Cd + Cs, 4, h, w), dtype=a.dtype, device=a.device)
+        lib = _lib.load()
+        with torch.cuda.device_of(a):
+            _call("tlerp_cat_fwd", tlerp_fwd_bytes(B, Cd, Cs, h * w, a.element_size()), lib.smow_tlerp_pair_cat_fwd,
+                  dec.data_ptr() if dec is not None else None, a.data_ptr(), b.data_ptr(), cat.data_ptr(),
+                  B, Cd, Cs, h * w, _dtype_code(a), _lib.NCDHW, _stream())
+        ctx.dims = (B, Cd, Cs, h, w)
+        return cat
+
+    @staticmethod
+    def backward(ctx, gcat):
+        B, Cd, Cs, h, w = ctx.dims
+        gcat = gcat.contiguous()
+        ga = torch.empty((B, Cs, h, w), dtype=gcat.dtype, device=gcat.device)
+        gb = torch.empty_like(ga)
+        lib = _lib.load()
+        with torch.cuda.device_of(gcat):
+            _call("tlerp_cat_bwd", tlerp_bwd_bytes(B, Cs, h * w, gcat.element_size()), lib.smow_tlerp_pair_cat_bwd,
+                  gcat.data_ptr(), ga.data_ptr(), gb.data_ptr(), B, Cd, Cs, h * w, _dtype_code(gcat),
+                  _lib.NCDHW, _stream())
+        gdec = gcat[:, :Cd] if Cd > 0 else None
+        return gdec, ga, gb
+
+
+def tlerp_cat(dec, skip):
+    """cat([dec, interpolate(skip, (4,h,w), trilinear, align_corners=True)], dim=1) in one launch."""
+    return _TLerpCat.apply(dec, skip)
+
+
+def tlerp(skip):
+    """Temporal 2 -> 4 upsample alone: (B,C,2,h,w) -> (B,C,4,h,w)."""
+    return _TLerpCat.apply(None, skip)
+
+
+def tlerp_pair_cat(dec, x_t1, x_t2):
+    """tlerp_cat on two un-stacked (B,C,h,w) frames (dec may be None)."""
+    return _TLerpPairCat.apply(dec, x_t1, x_t2)
