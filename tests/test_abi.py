@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads, exports every symbol include/smow_b200.h declares, and the Python
+operators refuse to run without CUDA (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import ROOT
+from smow_net_b200 import _lib, ops
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "smow_b200.h")).read()
+    return sorted(set(re.findall(r"\b(smow_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "build the extension: python -m smow_net_b200.build"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+
+
+def test_version_and_options_without_gpu():
+    lib = _lib.load()
+    assert lib.smow_abi_version() == _lib.ABI_VERSION
+    old = _lib.get_option("warp_fwd_variant")
+    _lib.set_option("warp_fwd_variant", 0)
+    assert _lib.get_option("warp_fwd_variant") == 0
+    _lib.set_option("warp_fwd_variant", old)
+    with pytest.raises(RuntimeError, match="unknown option"):
+        _lib.set_option("no_such_knob", 1)
+    assert _lib.get_option("no_such_knob") == -1
+    assert isinstance(_lib.launch_count(), int)
+
+
+def test_argument_errors_are_reported_not_thrown():
+    lib = _lib.load()
+    rc = lib.smow_warp_stack_fwd(None, None, None, None, None, 1, 4, 8, 8, 0, 0, None)
+    assert rc == -1 and b"null" in lib.smow_last_error()
+    rc = lib.smow_tlerp_cat_fwd(None, None, None, 1, 0, 4, 64, 0, 0, None)
+    assert rc == -1
+
+
+def test_operators_refuse_cpu_tensors():
+    x = torch.randn(1, 4, 2, 8, 8)
+    flow = torch.zeros(1, 2, 2, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.flow_warp(x, flow, (8, 8))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.tlerp(x)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.tlerp_pair_cat(None, x[:, :, 0], x[:, :, 1])
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsmow_b200.so")
+    with pytest.raises(RuntimeError, match="mandatory"):
+        _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "smow_net_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "liboracle" not in src, f
