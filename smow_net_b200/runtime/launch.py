@@ -1,0 +1,158 @@
+"""One-process-per-GPU launchers (torchrun): DDP training and collective-free sharded inference.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        -m smow_net_b200.runtime.launch train --model s --global-batch 128 --steps 50
+    ... -m smow_net_b200.runtime.launch infer --model s --tiles 64 --tile-size 1024
+
+The reference is single-GPU (train.py:2 pins CUDA_VISIBLE_DEVICES=0); this launcher is new functionality:
+image pairs are sharded by rank, gradients are all-reduced by DDP over NCCL/NVLink (BatchNorm stays
+per-replica, like the reference, so 8 x 16 pairs reproduces its batch-16 statistics), and inference
+replicas never communicate.
+"""
+import argparse
+import copy
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+from . import step as S
+from . import synthetic
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def init_distributed(backend=None):
+    rank, local_rank, world = dist_env()
+    use_cuda = torch.cuda.is_available()
+    if use_cuda:
+        torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kw = {}
+        if use_cuda and backend in (None, "nccl"):
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), rank=rank, world_size=world, **kw)
+    device = torch.device("cuda", local_rank) if use_cuda else torch.device("cpu")
+    return rank, local_rank, world, device
+
+
+def build_model(kind, device, pretrained=False):
+    from ..models import SMOW_Net, SMOW_Net_LW
+    if kind == "s":
+        import torchvision
+        weights = torchvision.models.ResNet18_Weights.DEFAULT if pretrained else None
+        model = SMOW_Net(copy.deepcopy(torchvision.models.resnet18(weights=weights)))
+    elif kind == "lw":
+        model = S.freeze_unused(SMOW_Net_LW(pretrained=pretrained))
+    else:
+        raise ValueError("model must be 's' (SMOW_Net) or 'lw' (SMOW_Net_LW)")
+    return model.to(device)
+
+
+def wrap_ddp(model, device, world):
+    if world == 1:
+        return model
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    ids = [device.index] if device.type == "cuda" else None
+    # per-replica BatchNorm statistics (no SyncBN, no buffer broadcast) — the reference's regime
+    return DDP(model, device_ids=ids, broadcast_buffers=False, gradient_as_bucket_view=True)
+
+
+def max_over_ranks(value, device, world):
+    if world == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def train(args):
+    rank, local_rank, world, device = init_distributed()
+    synthetic.seed_everything(2022, rank)
+    lo, hi = synthetic.shard_range(args.global_batch, rank, world)
+    model = wrap_ddp(build_model(args.model, device), device, world).train()
+    opt = S.make_optimizer(model)
+    sched = S.make_scheduler(opt, args.steps + args.warmup)
+    a, b, y = synthetic.make_batch(hi - lo, device=device, seed=2022 + rank)
+    for _ in range(args.warmup):
+        S.train_step(model, opt, sched, a, b, y)
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = S.train_step(model, opt, sched, a, b, y)
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0, device, world)
+    if rank == 0:
+        print(json.dumps({"mode": "train", "model": args.model, "n_gpus": world, "global_batch": args.global_batch,
+                          "steps": args.steps, "ms_per_step": 1e3 * dt / max(1, args.steps),
+                          "pairs_per_s": args.global_batch * args.steps / dt, "loss": float(loss)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@torch.no_grad()
+def infer(args):
+    """Config 4: `tiles` scene tiles of tile_size^2, contiguous shards per rank, 256^2 crops, no collectives
+    in the data path (one MAX all-reduce of the elapsed time for reporting only)."""
+    rank, local_rank, world, device = init_distributed()
+    model = build_model(args.model, device).eval()
+    lo, hi = synthetic.shard_range(args.tiles, rank, world)
+    g = torch.Generator().manual_seed(2022 + rank)
+    n_changed, t_total = 0, 0.0
+    for i in range(args.warmup + 1):
+        if device.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_changed = 0
+        for s in range(lo, hi, args.tiles_per_batch):
+            n = min(args.tiles_per_batch, hi - s)
+            ta = torch.randn(n, 3, args.tile_size, args.tile_size, generator=g).to(device, non_blocking=True)
+            tb = torch.randn(n, 3, args.tile_size, args.tile_size, generator=g).to(device, non_blocking=True)
+            prob = model(synthetic.tiles_to_crops(ta), synthetic.tiles_to_crops(tb))
+            mask = synthetic.crops_to_tiles(prob > 0.5, n, args.tile_size, args.tile_size)   # test.py:134 threshold
+            n_changed += int(mask.sum())
+        if device.type == "cuda":
+            torch.cuda.synchronize()
+        t_total = time.perf_counter() - t0
+    dt = max_over_ranks(t_total, device, world)
+    crops = args.tiles * (args.tile_size // 256) ** 2
+    if rank == 0:
+        print(json.dumps({"mode": "infer", "model": args.model, "n_gpus": world, "tiles": args.tiles,
+                          "tile_size": args.tile_size, "pairs_per_s": crops / dt, "s_total": dt,
+                          "changed_px_rank0": n_changed}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    sub = ap.add_subparsers(dest="mode", required=True)
+    t = sub.add_parser("train")
+    t.add_argument("--model", default="s", choices=["s", "lw"])
+    t.add_argument("--global-batch", type=int, default=128)
+    t.add_argument("--steps", type=int, default=20)
+    t.add_argument("--warmup", type=int, default=3)
+    t.set_defaults(fn=train)
+    i = sub.add_parser("infer")
+    i.add_argument("--model", default="s", choices=["s", "lw"])
+    i.add_argument("--tiles", type=int, default=64)
+    i.add_argument("--tile-size", type=int, default=1024)
+    i.add_argument("--tiles-per-batch", type=int, default=2)
+    i.add_argument("--warmup", type=int, default=1)
+    i.set_defaults(fn=infer)
+    args = ap.parse_args(argv)
+    args.fn(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""GPU: the drop-in modules end to end on the CUDA kernels, against the real reference's golden
+outputs (generated on the CPU by oracle/model_fixture.py) and against the oracle-routed module on the
+same device.  TF32 is disabled so cuDNN/cuBLAS stay comparable with the CPU reference."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle.model_fixture import run_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+class _OnDevice(torch.nn.Module):
+    """run_model() works on CPU tensors; this wrapper moves I/O so the fixture code is shared."""
+
+    def __init__(self, m):
+        super().__init__()
+        self.m = m
+
+    def forward(self, a, b):
+        return self.m(a.to(DEV), b.to(DEV)).cpu()
+
+    def named_parameters(self, *a, **k):
+        return ((n, _CpuGrad(p)) for n, p in self.m.named_parameters())
+
+    def named_buffers(self, *a, **k):
+        return ((n, b.detach().cpu()) for n, b in self.m.named_buffers())
+
+
+class _CpuGrad:
+    def __init__(self, p):
+        self.grad = None if p.grad is None else p.grad.detach().cpu()
+
+
+@pytest.mark.parametrize("kind", ["lw", "s"])
+def test_module_on_cuda_matches_reference_golden(kind):
+    from smow_net_b200 import _lib
+    model = helpers.seeded_model(kind, device=DEV)
+    x1, x2 = helpers.seeded_pair(2)
+    before = _lib.launch_count()
+    got = run_model(_OnDevice(model), x1, x2, helpers.seeded_labels(2))
+    assert _lib.launch_count() - before >= 14   # the hand-written kernels really ran
+    want = helpers.load_golden("model_%s.npz" % kind)
+    for k in want.files:
+        a, b = want[k], got[k]
+        if a.dtype == np.uint8:
+            diff = int(np.unpackbits(a ^ b).sum())
+            assert diff <= 0.001 * a.size * 8, (k, diff)          # change maps: <= 0.1 % of pixels differ
+        elif k.startswith("grad/") or k == "loss" or k.startswith("bn/"):
+            err = np.abs(a.astype(np.float64) - b).max() / max(1e-12, np.abs(a).max())
+            assert err < 2e-3, (k, err)                            # different conv algorithms CPU vs cuDNN
+        else:
+            assert np.abs(a - b).max() <= 1e-4, (k, np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("kind", ["lw", "s"])
+def test_module_matches_oracle_routed_module_on_same_device(kind, monkeypatch):
+    """Same weights, same device, same cuDNN: only the hot-path operators differ."""
+    model = helpers.seeded_model(kind, device=DEV).eval()
+    x1, x2 = (t.to(DEV) for t in helpers.seeded_pair(2, seed=3))
+    with torch.no_grad():
+        mine = model(x1, x2)
+    helpers.use_oracle_ops(monkeypatch)
+    with torch.no_grad():
+        ref = model(x1, x2)
+    assert float((mine - ref).abs().max()) <= 1e-5
+    assert float(((mine > 0.5) != (ref > 0.5)).float().mean()) <= 1e-3

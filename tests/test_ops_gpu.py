@@ -1,0 +1,214 @@
+"""GPU: the CUDA kernels, called through the C ABI (smow_net_b200.ops -> libsmow_b200.so), against
+  (1) golden vectors produced by the real reference,
+  (2) the oracle's torch restatement of the reference run on the same device (= ATen's own CUDA path),
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerance (north_star): max-abs <= 1e-5 in fp32 for unit-scale tensors (gradients whose magnitude
+exceeds 1 are compared relative to their max), <= 2e-2 for bf16 storage."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden_cases
+from oracle import torch_ref
+from smow_net_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FWD_VARIANTS = [0, 1]
+BWD_VARIANTS = [0]   # + [1] once the tiled backward kernel is built
+
+
+def _scale(t):
+    return max(1.0, float(t.abs().max()))
+
+
+@pytest.fixture
+def variants():
+    saved = {k: _lib.get_option(k) for k in ("warp_fwd_variant", "warp_bwd_variant")}
+    yield
+    for k, v in saved.items():
+        _lib.set_option(k, v)
+
+
+def run_warp(x, flow, gout):
+    x = x.detach().clone().requires_grad_(True)
+    flow = flow.detach().clone().requires_grad_(True)
+    out = ops.flow_warp(x, flow, x.shape[3:])
+    out.backward(gout)
+    return out.detach(), x.grad.detach(), flow.grad.detach()
+
+
+def check_warp(got, want, tol=1e-5):
+    for name, a, b in zip(("out", "gx", "gflow"), got, want):
+        err = float((a.float() - b.float()).abs().max())
+        assert err <= tol * _scale(b.float()), "%s: max-abs error %.3e (scale %.2f)" % (name, err, _scale(b.float()))
+
+
+@pytest.mark.parametrize("bv", BWD_VARIANTS)
+@pytest.mark.parametrize("fv", FWD_VARIANTS)
+@pytest.mark.parametrize("name", golden_cases("warp")[1])
+def test_warp_against_reference_golden(name, fv, bv, variants):
+    _lib.set_option("warp_fwd_variant", fv)
+    _lib.set_option("warp_bwd_variant", bv)
+    z, _ = golden_cases("warp")
+    g = lambda k: torch.from_numpy(z["warp/%s/%s" % (name, k)]).to(DEV)
+    got = run_warp(g("x"), g("flow"), g("gout"))
+    check_warp(got, (g("out"), g("gx"), g("gflow")))
+    assert torch.equal(got[0][:, :, 0], g("x")[:, :, 0]) and torch.equal(got[0][:, :, 3], g("x")[:, :, 1])
+
+
+# (B, C, H, W, sigma): the two models' OFW shapes, sweep corners, ragged shapes, large displacement
+FULL_CASES = [(4, 32, 128, 128, 0.3), (4, 16, 128, 128, 0.3), (2, 64, 64, 64, 8.0), (1, 128, 256, 256, 0.3),
+              (2, 256, 64, 64, 0.3), (3, 8, 40, 72, 2.0), (2, 5, 17, 23, 1.0), (1, 4, 128, 128, 40.0),
+              (2, 12, 100, 128, 3.0)]
+
+
+@pytest.mark.parametrize("bv", BWD_VARIANTS)
+@pytest.mark.parametrize("fv", FWD_VARIANTS)
+@pytest.mark.parametrize("case", FULL_CASES)
+def test_warp_against_same_device_reference(case, fv, bv, variants):
+    _lib.set_option("warp_fwd_variant", fv)
+    _lib.set_option("warp_bwd_variant", bv)
+    B, C, H, W, sigma = case
+    g = torch.Generator(device=DEV).manual_seed(B * 1000 + C)
+    x = torch.randn(B, C, 2, H, W, device=DEV, generator=g)
+    flow = torch.randn(B, 2, 2, H, W, device=DEV, generator=g) * sigma
+    gout = torch.randn(B, C, 4, H, W, device=DEV, generator=g)
+    check_warp(run_warp(x, flow, gout), torch_ref.warp_with_grads(x, flow, gout))
+
+
+@pytest.mark.parametrize("fv", FWD_VARIANTS)
+def test_warp_forward_is_bit_exact_vs_aten_cuda(fv, variants):
+    """The coordinate chain is reproduced bit for bit, and the 4-tap accumulation uses ATen's order."""
+    _lib.set_option("warp_fwd_variant", fv)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(2, 32, 2, 128, 128, device=DEV, generator=g)
+    flow = torch.randn(2, 2, 2, 128, 128, device=DEV, generator=g) * 1.5
+    with torch.no_grad():
+        mine, ref = ops.flow_warp(x, flow, (128, 128)), torch_ref.ref_flow_warp(x, flow)
+    assert float((mine - ref).abs().max()) <= 1e-6
+    assert float((mine != ref).float().mean()) < 1e-3   # essentially every element identical
+
+
+@pytest.mark.parametrize("bv", BWD_VARIANTS)
+@pytest.mark.parametrize("fv", FWD_VARIANTS)
+def test_warp_bf16_storage(fv, bv, variants):
+    """bf16 features, fp32 flow/coordinates/accumulation; oracle = fp32 reference on bf16-rounded
+    features (SURVEY §7 'bf16': the reference's own bf16 path quantises the grid and is unusable)."""
+    _lib.set_option("warp_fwd_variant", fv)
+    _lib.set_option("warp_bwd_variant", bv)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(2, 32, 2, 128, 128, device=DEV, generator=g).bfloat16()
+    flow = torch.randn(2, 2, 2, 128, 128, device=DEV, generator=g) * 0.3
+    gout = torch.randn(2, 32, 4, 128, 128, device=DEV, generator=g).bfloat16()
+    got = run_warp(x, flow, gout)
+    want = torch_ref.warp_with_grads(x.float(), flow, gout.float())
+    assert got[0].dtype == torch.bfloat16 and got[1].dtype == torch.bfloat16 and got[2].dtype == torch.float32
+    assert float((got[0].float() - want[0]).abs().max()) <= 2e-2
+    if bv == 1:  # variant 0 accumulates the scatter in bf16 atomics; the tiled kernel accumulates in fp32
+        assert float((got[1].float() - want[1]).abs().max()) <= 2e-2 * _scale(want[1])
+    assert float((got[2] - want[2]).abs().max()) <= 1e-4 * _scale(want[2])
+
+
+def test_warp_pair_equals_stacked(variants):
+    g = torch.Generator(device=DEV).manual_seed(5)
+    a = torch.randn(3, 16, 128, 128, device=DEV, generator=g)
+    b = torch.randn(3, 16, 128, 128, device=DEV, generator=g)
+    flow = torch.randn(3, 2, 2, 128, 128, device=DEV, generator=g)
+    gout = torch.randn(3, 16, 4, 128, 128, device=DEV, generator=g)
+    ar, br, fr = (t.clone().requires_grad_(True) for t in (a, b, flow))
+    out = ops.warp_pair(ar, br, fr)
+    out.backward(gout)
+    ref = run_warp(torch.stack((a, b), 2), flow, gout)
+    assert torch.equal(out.detach(), ref[0])
+    assert float((ar.grad - ref[1][:, :, 0]).abs().max()) <= 1e-5 and float((br.grad - ref[1][:, :, 1]).abs().max()) <= 1e-5
+    assert float((fr.grad - ref[2]).abs().max()) <= 1e-5 * _scale(ref[2])
+
+
+@pytest.mark.parametrize("fv", FWD_VARIANTS)
+def test_warp_properties_at_full_size(fv, variants):
+    """Config 3's per-GPU shape (B=16, C=32, 128x128): linearity in x, exact pass-through slots,
+    adjoint identity <warp(x), g> == <x, warp^T(g)> between the forward and backward kernels."""
+    _lib.set_option("warp_fwd_variant", fv)
+    g = torch.Generator(device=DEV).manual_seed(8)
+    x = torch.randn(16, 32, 2, 128, 128, device=DEV, generator=g)
+    y = torch.randn(16, 32, 2, 128, 128, device=DEV, generator=g)
+    flow = torch.randn(16, 2, 2, 128, 128, device=DEV, generator=g) * 0.5
+    gout = torch.randn(16, 32, 4, 128, 128, device=DEV, generator=g)
+    with torch.no_grad():
+        wx, wy, wxy = (ops.flow_warp(t, flow, (128, 128)) for t in (x, y, x + y))
+    assert float((wx + wy - wxy).abs().max()) <= 5e-6
+    assert torch.equal(wx[:, :, 0], x[:, :, 0]) and torch.equal(wx[:, :, 3], x[:, :, 1])
+    for bv in BWD_VARIANTS:
+        _lib.set_option("warp_bwd_variant", bv)
+        _, gx, _ = run_warp(x, flow, gout)
+        lhs = float((wx.double() * gout.double()).sum())
+        rhs = float((x.double() * gx.double()).sum())
+        assert abs(lhs - rhs) <= 1e-6 * max(1.0, abs(lhs)) + 1e-2, (lhs, rhs)
+
+
+def test_warp_argument_errors():
+    x = torch.randn(1, 4, 2, 8, 8, device=DEV)
+    with pytest.raises(RuntimeError, match="flow must be"):
+        ops.flow_warp(x, torch.zeros(1, 2, 2, 8, 9, device=DEV), (8, 8))
+    with pytest.raises(RuntimeError, match="must equal"):
+        ops.flow_warp(x, torch.zeros(1, 2, 2, 8, 8, device=DEV), (16, 16))
+    with pytest.raises(RuntimeError, match="unsupported dtype"):
+        ops.flow_warp(x.half(), torch.zeros(1, 2, 2, 8, 8, device=DEV), (8, 8))
+
+
+# ---------------------------------------------------------------------------------- tlerp + concat
+@pytest.mark.parametrize("name", golden_cases("tlerp")[1])
+def test_tlerp_against_reference_golden(name):
+    z, _ = golden_cases("tlerp")
+    has_dec = ("tlerp/%s/dec" % name) in z.files
+    g = lambda k: torch.from_numpy(z["tlerp/%s/%s" % (name, k)]).to(DEV)
+    skip = g("skip").requires_grad_(True)
+    dec = g("dec").requires_grad_(True) if has_dec else None
+    cat = ops.tlerp_cat(dec, skip)
+    cat.backward(g("gcat"))
+    assert float((cat.detach() - g("cat")).abs().max()) <= 1e-6
+    assert float((skip.grad - g("gskip")).abs().max()) <= 2e-6
+    cd = dec.shape[1] if has_dec else 0
+    assert torch.equal(cat[:, cd:, 0], skip[:, :, 0]) and torch.equal(cat[:, cd:, 3], skip[:, :, 1])
+    if has_dec:
+        assert torch.equal(dec.grad, g("gdec")) and torch.equal(cat[:, :cd].detach(), g("dec"))
+
+
+# the five scales of both models (Cd, Cs, h) + ragged shapes
+TLERP_CASES = [(32, 32, 128), (64, 32, 64), (64, 64, 32), (128, 128, 16), (256, 256, 8), (28, 16, 128), (32, 24, 64),
+               (320, 320, 8), (0, 256, 8), (3, 5, 7), (0, 1, 3)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", TLERP_CASES)
+def test_tlerp_against_same_device_reference(case, dtype):
+    Cd, Cs, h = case
+    B = 3
+    g = torch.Generator(device=DEV).manual_seed(Cd + Cs + h)
+    skip = torch.randn(B, Cs, 2, h, h, device=DEV, generator=g).to(dtype)
+    dec = torch.randn(B, Cd, 4, h, h, device=DEV, generator=g).to(dtype) if Cd else None
+    gcat = torch.randn(B, Cd + Cs, 4, h, h, device=DEV, generator=g).to(dtype)
+    s1 = skip.clone().requires_grad_(True)
+    d1 = dec.clone().requires_grad_(True) if Cd else None
+    cat = ops.tlerp_cat(d1, s1)
+    cat.backward(gcat)
+    want = torch_ref.tlerp_cat_with_grads(None if dec is None else dec.float(), skip.float(), gcat.float())
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    assert float((cat.detach().float() - want[0]).abs().max()) <= tol
+    assert float((s1.grad.float() - want[2]).abs().max()) <= (2e-6 if dtype == torch.float32 else 4e-2)
+    if Cd:
+        assert torch.equal(d1.grad.float(), want[1])
+    # un-stacked frames give the same bits
+    a, b = skip[:, :, 0].contiguous().requires_grad_(True), skip[:, :, 1].contiguous().requires_grad_(True)
+    cat2 = ops.tlerp_pair_cat(dec, a, b)
+    cat2.backward(gcat)
+    assert torch.equal(cat2.detach(), cat.detach())
+    assert torch.equal(a.grad, s1.grad[:, :, 0]) and torch.equal(b.grad, s1.grad[:, :, 1])
+
+
+def test_launch_counter_counts_our_kernels():
+    x = torch.randn(1, 4, 2, 16, 16, device=DEV)
+    before = _lib.launch_count()
+    ops.tlerp(x)
+    assert _lib.launch_count() == before + 1
