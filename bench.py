@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--model", default=MODEL, choices=["lw", "s"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strict-fp32", action="store_true", help="disable cuDNN TF32 convolutions")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="ncu helper: warm up, then run --steps steps between cudaProfilerStart/Stop and exit")
     return ap.parse_args()
 
 
@@ -153,6 +155,14 @@ def main():
     for _ in range(max(3, args.warmup)):
         S.fwd_bwd(model, a, b, y)
     sync_all()
+    if args.profile_step:      # for `ncu --profile-from-start off`: exactly the timed steps are captured
+        torch.cuda.profiler.start()
+        for _ in range(args.steps):
+            S.fwd_bwd(model, a, b, y)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile_step": True, "steps": args.steps}))
+        return
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()

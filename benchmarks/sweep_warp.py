@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""Isolated hot-path kernel sweep (BASELINE.json configs[4]): warp+stack fwd/bwd and tlerp+concat
+fwd/bwd, HBM-cold (working set >= --min-bytes, several times the 126 MB L2), CUDA-event timed, against the
+reference's own op sequence on the same GPU (oracle.torch_ref: F.grid_sample/F.interpolate/torch.cat =
+ATen's sm_100 kernels).
+
+    python benchmarks/sweep_warp.py [--quick] [--out gpurun_out/sweep.jsonl]
+
+One JSON line per (op, shape, dtype, variant): ms (median), algorithmic GB/s, fraction of the measured
+HBM peak, and the speed-up over the ATen sequence.  This script is measurement infrastructure: it may
+import oracle/ (as the baseline being compared against), the product never does.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from oracle import torch_ref  # noqa: E402
+from smow_net_b200 import _lib, ops  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def time_fn(fn, warm, iters):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def pick_batch(bytes_per_pair, min_bytes, cap=512):
+    return int(max(1, min(cap, -(-min_bytes // bytes_per_pair))))
+
+
+def sweep_warp(args, emit):
+    dev = "cuda:0"
+    shapes = [(16, 128), (32, 128)] + [(c, h) for c in (64, 128, 256) for h in (64, 128, 256)]
+    if args.quick:
+        shapes = [(16, 128), (32, 128), (64, 128), (256, 64)]
+    for dtype in (torch.float32, torch.bfloat16):
+        s = 4 if dtype == torch.float32 else 2
+        for C, H in shapes:
+            W = H
+            for sigma in (0.3, 8.0):
+                if sigma == 8.0 and (args.quick or C not in (32, 64)):
+                    continue
+                per_pair = ops.warp_bwd_bytes(1, C, H, W, s)
+                B = pick_batch(per_pair, args.min_bytes)
+                g = torch.Generator(device=dev).manual_seed(1)
+                x = torch.randn(B, C, 2, H, W, device=dev, generator=g).to(dtype)
+                flow = torch.randn(B, 2, 2, H, W, device=dev, generator=g) * sigma
+                gout = torch.randn(B, C, 4, H, W, device=dev, generator=g).to(dtype)
+                base = {"C": C, "H": H, "W": W, "B": B, "dtype": str(dtype).split(".")[-1], "sigma": sigma}
+                # reference sequence (fp32 only: its bf16 path quantises the grid)
+                ref_f = ref_b = None
+                if dtype == torch.float32:
+                    xr, fr = x.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+                    with torch.no_grad():
+                        ref_f = time_fn(lambda: torch_ref.ref_flow_warp(x, flow), args.warm, args.iters)
+
+                    def ref_fb():
+                        xr.grad = fr.grad = None
+                        torch_ref.ref_flow_warp(xr, fr).backward(gout)
+                    ref_b = time_fn(ref_fb, args.warm, args.iters) - ref_f
+                for fv in (0, 1):
+                    _lib.set_option("warp_fwd_variant", fv)
+                    with torch.no_grad():
+                        ms = time_fn(lambda: ops.flow_warp(x, flow, (H, W)), args.warm, args.iters)
+                    nb = ops.warp_fwd_bytes(B, C, H, W, s)
+                    emit(dict(base, op="warp_stack_fwd", variant=fv, ms=ms, gbps=nb / ms / 1e6,
+                              frac=nb / ms / 1e6 / peak(), ref_ms=ref_f, speedup=(ref_f / ms) if ref_f else None))
+                xg, fg = x.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+                out = ops.flow_warp(xg, fg, (H, W))
+                for bv in args.bwd_variants:
+                    _lib.set_option("warp_bwd_variant", bv)
+
+                    def bwd():
+                        xg.grad = fg.grad = None
+                        out.backward(gout, retain_graph=True)
+                    ms = time_fn(bwd, args.warm, args.iters)
+                    nb = ops.warp_bwd_bytes(B, C, H, W, s)
+                    emit(dict(base, op="warp_stack_bwd", variant=bv, ms=ms, gbps=nb / ms / 1e6,
+                              frac=nb / ms / 1e6 / peak(), ref_ms=ref_b, speedup=(ref_b / ms) if ref_b else None))
+                del x, flow, gout, out, xg, fg
+                torch.cuda.empty_cache()
+
+
+def sweep_tlerp(args, emit):
+    dev = "cuda:0"
+    # (Cd, Cs, h): the two models' five decoder levels
+    shapes = [(32, 32, 128), (64, 32, 64), (64, 64, 32), (128, 128, 16), (256, 256, 8), (28, 16, 128), (32, 24, 64)]
+    if args.quick:
+        shapes = shapes[:2]
+    for dtype in (torch.float32, torch.bfloat16):
+        s = 4 if dtype == torch.float32 else 2
+        for Cd, Cs, h in shapes:
+            per_pair = ops.tlerp_fwd_bytes(1, Cd, Cs, h * h, s)
+            B = pick_batch(per_pair, args.min_bytes, cap=8192)
+            g = torch.Generator(device=dev).manual_seed(2)
+            skip = torch.randn(B, Cs, 2, h, h, device=dev, generator=g).to(dtype)
+            dec = torch.randn(B, Cd, 4, h, h, device=dev, generator=g).to(dtype)
+            gcat = torch.randn(B, Cd + Cs, 4, h, h, device=dev, generator=g).to(dtype)
+            base = {"Cd": Cd, "Cs": Cs, "h": h, "B": B, "dtype": str(dtype).split(".")[-1]}
+            with torch.no_grad():
+                ref_f = time_fn(lambda: torch_ref.ref_tlerp_cat(dec, skip), args.warm, args.iters)
+                ms = time_fn(lambda: ops.tlerp_cat(dec, skip), args.warm, args.iters)
+            nb = ops.tlerp_fwd_bytes(B, Cd, Cs, h * h, s)
+            emit(dict(base, op="tlerp_cat_fwd", variant=0, ms=ms, gbps=nb / ms / 1e6, frac=nb / ms / 1e6 / peak(),
+                      ref_ms=ref_f, speedup=ref_f / ms))
+            sg = skip.clone().requires_grad_(True)
+            cat = ops.tlerp_cat(dec, sg)
+
+            def bwd():
+                sg.grad = None
+                cat.backward(gcat, retain_graph=True)
+            ms = time_fn(bwd, args.warm, args.iters)
+            sr = skip.clone().requires_grad_(True)
+            catr = torch_ref.ref_tlerp_cat(dec, sr)
+
+            def rbwd():
+                sr.grad = None
+                catr.backward(gcat, retain_graph=True)
+            ref_b = time_fn(rbwd, args.warm, args.iters)
+            nb = ops.tlerp_bwd_bytes(B, Cs, h * h, s)
+            emit(dict(base, op="tlerp_cat_bwd", variant=0, ms=ms, gbps=nb / ms / 1e6, frac=nb / ms / 1e6 / peak(),
+                      ref_ms=ref_b, speedup=ref_b / ms))
+            del skip, dec, gcat, cat, catr
+            torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", choices=["", "warp", "tlerp"])
+    ap.add_argument("--min-bytes", type=int, default=1 << 30)
+    ap.add_argument("--warm", type=int, default=5)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--bwd-variants", type=int, nargs="+", default=[0, 1])
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
+    args = ap.parse_args()
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    fh = open(args.out, "w")
+
+    def emit(rec):
+        line = json.dumps(rec)
+        fh.write(line + "\n")
+        fh.flush()
+        print(line)
+    saved = {k: _lib.get_option(k) for k in ("warp_fwd_variant", "warp_bwd_variant")}
+    if args.only in ("", "warp"):
+        sweep_warp(args, emit)
+    if args.only in ("", "tlerp"):
+        sweep_tlerp(args, emit)
+    for k, v in saved.items():
+        _lib.set_option(k, v)
+
+
+if __name__ == "__main__":
+    main()
