@@ -177,8 +177,10 @@ static int bwd_impl(const T* gout, const T* x1, const T* x2, int64_t sB, int64_t
   if (layout == SMOW_NDHWC)
     return warp_bwd_ndhwc<T>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, st);
   const int variant = option(OPT_WARP_BWD_VARIANT);
-  if (variant == 1 && tiled_shape_ok<T>(x1, x2, gout, sB, sC, C, H, W) && aligned16(gx1) && aligned16(gx2))
-    return warp_bwd_tiled<T>(gout, x1, x2, sB, sC, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, st);
+  if (variant == 1 && tiled_shape_ok<T>(x1, x2, gout, sB, sC, C, H, W) && aligned16(gx1) && aligned16(gx2)) {
+    const int rc = warp_bwd_tiled<T>(gout, x1, x2, sB, sC, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, st);
+    if (rc != SMOW_ERANGE) return rc;   // rows too wide for one tile: the scatter kernel below handles them
+  }
   if (variant != 0 && variant != 1) return fail(SMOW_EINVAL, "unknown warp_bwd_variant %d", variant);
   if ((int64_t)B * C > 65535) return fail(SMOW_ERANGE, "B*C too large for variant 0");
   Frames<const T> x{x1, x2, sB, sC};

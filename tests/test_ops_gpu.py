@@ -15,7 +15,7 @@ from smow_net_b200 import _lib, ops
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 FWD_VARIANTS = [0, 1]
-BWD_VARIANTS = [0]   # + [1] once the tiled backward kernel is built
+BWD_VARIANTS = [0, 1]
 
 
 def _scale(t):
@@ -145,6 +145,39 @@ def test_warp_properties_at_full_size(fv, variants):
         lhs = float((wx.double() * gout.double()).sum())
         rhs = float((x.double() * gx.double()).sum())
         assert abs(lhs - rhs) <= 1e-6 * max(1.0, abs(lhs)) + 1e-2, (lhs, rhs)
+
+
+@pytest.mark.parametrize("bv", BWD_VARIANTS)
+def test_warp_backward_converging_and_far_flows(bv, variants):
+    """Backward edge cases of the inverse-gather kernel: many sources landing on one target pixel
+    (register list overflow), sources far outside the tile window (atomic side kernel), mixed with
+    ordinary sub-pixel flow."""
+    _lib.set_option("warp_bwd_variant", bv)
+    B, C, H, W = 2, 8, 64, 128
+    g = torch.Generator(device=DEV).manual_seed(21)
+    x = torch.randn(B, C, 2, H, W, device=DEV, generator=g)
+    gout = torch.randn(B, C, 4, H, W, device=DEV, generator=g)
+    ws = torch.arange(W, device=DEV, dtype=torch.float32).view(1, 1, 1, W)
+    hs = torch.arange(H, device=DEV, dtype=torch.float32).view(1, 1, H, 1)
+    flow = torch.randn(B, 2, 2, H, W, device=DEV, generator=g) * 0.3
+    # pair 0, frame 0: every pixel samples (almost) the same point -> hundreds of sources per target
+    flow[0, 0, 0] = ((W / 2 + 0.37) - ws) * 2 * W / (W - 1)
+    flow[0, 1, 0] = ((H / 2 + 0.61) - hs) * 2 * H / (H - 1)
+    # pair 1, frame 1: a 20-row / 9-column shear, far beyond HALO / DCAP
+    flow[1, 0, 1] += 18.0
+    flow[1, 1, 1] += 40.0
+    check_warp(run_warp(x, flow, gout), torch_ref.warp_with_grads(x, flow, gout), tol=2e-5)
+
+
+def test_warp_backward_is_deterministic(variants):
+    """The tiled backward sums in a fixed order (ATen's atomics do not)."""
+    _lib.set_option("warp_bwd_variant", 1)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x = torch.randn(4, 32, 2, 128, 128, device=DEV, generator=g)
+    flow = torch.randn(4, 2, 2, 128, 128, device=DEV, generator=g) * 0.8
+    gout = torch.randn(4, 32, 4, 128, 128, device=DEV, generator=g)
+    a, b = run_warp(x, flow, gout), run_warp(x, flow, gout)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
 
 
 def test_warp_argument_errors():
