@@ -79,7 +79,7 @@ def sweep_warp(args, emit):
                         xr.grad = fr.grad = None
                         torch_ref.ref_flow_warp(xr, fr).backward(gout)
                     ref_b = time_fn(ref_fb, args.warm, args.iters) - ref_f
-                for fv in (0, 1):
+                for fv in args.fwd_variants:
                     _lib.set_option("warp_fwd_variant", fv)
                     with torch.no_grad():
                         ms = time_fn(lambda: ops.flow_warp(x, flow, (H, W)), args.warm, args.iters)
@@ -152,7 +152,8 @@ def main():
     ap.add_argument("--min-bytes", type=int, default=1 << 30)
     ap.add_argument("--warm", type=int, default=5)
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--bwd-variants", type=int, nargs="+", default=[0, 1])
+    ap.add_argument("--bwd-variants", type=int, nargs="+", default=[0, 1, 2])
+    ap.add_argument("--fwd-variants", type=int, nargs="+", default=[0, 1, 2])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

@@ -8,6 +8,7 @@
 // through L1 (what ATen does, minus its 30 helper launches); backward scatters with
 // L2 atomics.  It is the simple cross-check for the tiled variants in
 // warp_stack_tiled.cuh (bulk-copy staged tiles, inverse-gather backward).
+#include <type_traits>
 #include "common.cuh"
 #include "warp_stack_tiled.cuh"
 
@@ -158,10 +159,16 @@ static int fwd_impl(const T* x1, const T* x2, int64_t sB, int64_t sC, const floa
                     int layout, cudaStream_t st) {
   if (layout == SMOW_NDHWC) return warp_fwd_ndhwc<T>(x1, x2, sB, flow, xs, ys, out, B, C, H, W, st);
   const int variant = option(OPT_WARP_FWD_VARIANT);
-  if (variant != 0 && variant != 1) return fail(SMOW_EINVAL, "unknown warp_fwd_variant %d", variant);
-  // the tiled kernel needs whole 16 B rows; odd shapes take the direct kernel (same results)
-  if (variant == 1 && tiled_shape_ok<T>(x1, x2, out, sB, sC, C, H, W))
-    return warp_fwd_tiled<T>(x1, x2, sB, sC, flow, xs, ys, out, B, C, H, W, st);
+  if (variant < 0 || variant > 2) return fail(SMOW_EINVAL, "unknown warp_fwd_variant %d", variant);
+  // the tile kernels need whole 16 B rows; odd shapes take the direct kernel (same results)
+  const bool tile_ok = tiled_shape_ok<T>(x1, x2, out, sB, sC, C, H, W);
+  if constexpr (std::is_same<T, float>::value) {
+    if (variant == 2 && tile_ok) {
+      const int rc = warp_fwd_cvec(x1, x2, sB, sC, flow, xs, ys, out, B, C, H, W, st);
+      if (rc != SMOW_ERANGE) return rc;
+    }
+  }
+  if (variant >= 1 && tile_ok) return warp_fwd_tiled<T>(x1, x2, sB, sC, flow, xs, ys, out, B, C, H, W, st);
   Frames<const T> x{x1, x2, sB, sC};
   dim3 grid((H * W + 255) / 256, 2 * B);
   warp_stack_fwd_direct<T><<<grid, 256, 0, st>>>(x, flow, xs, ys, out, C, H, W);
@@ -177,11 +184,18 @@ static int bwd_impl(const T* gout, const T* x1, const T* x2, int64_t sB, int64_t
   if (layout == SMOW_NDHWC)
     return warp_bwd_ndhwc<T>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, st);
   const int variant = option(OPT_WARP_BWD_VARIANT);
-  if (variant == 1 && tiled_shape_ok<T>(x1, x2, gout, sB, sC, C, H, W) && aligned16(gx1) && aligned16(gx2)) {
+  const bool tile_ok = tiled_shape_ok<T>(x1, x2, gout, sB, sC, C, H, W) && aligned16(gx1) && aligned16(gx2);
+  if constexpr (std::is_same<T, float>::value) {
+    if (variant == 2 && tile_ok) {
+      const int rc = warp_bwd_cvec(gout, x1, x2, sB, sC, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, st);
+      if (rc != SMOW_ERANGE) return rc;
+    }
+  }
+  if (variant >= 1 && tile_ok) {
     const int rc = warp_bwd_tiled<T>(gout, x1, x2, sB, sC, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, st);
     if (rc != SMOW_ERANGE) return rc;   // rows too wide for one tile: the scatter kernel below handles them
   }
-  if (variant != 0 && variant != 1) return fail(SMOW_EINVAL, "unknown warp_bwd_variant %d", variant);
+  if (variant < 0 || variant > 2) return fail(SMOW_EINVAL, "unknown warp_bwd_variant %d", variant);
   if ((int64_t)B * C > 65535) return fail(SMOW_ERANGE, "B*C too large for variant 0");
   Frames<const T> x{x1, x2, sB, sC};
   Frames<T> gx{gx1, gx2, sB, sC};

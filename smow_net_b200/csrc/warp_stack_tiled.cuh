@@ -219,6 +219,12 @@ template <typename T>
 int warp_bwd_tiled(const T* gout, const T* x1, const T* x2, int64_t sB, int64_t sC, const float* flow,
                    const float* xs, const float* ys, T* gx1, T* gx2, float* gflow, int B, int C, int H, int W,
                    cudaStream_t st);
+// channel-vectorised variant 2 (fp32 only; SMOW_ERANGE = shape not covered, caller falls back)
+int warp_fwd_cvec(const float* x1, const float* x2, int64_t sB, int64_t sC, const float* flow, const float* xs,
+                  const float* ys, float* out, int B, int C, int H, int W, cudaStream_t st);
+int warp_bwd_cvec(const float* gout, const float* x1, const float* x2, int64_t sB, int64_t sC, const float* flow,
+                  const float* xs, const float* ys, float* gx1, float* gx2, float* gflow, int B, int C, int H,
+                  int W, cudaStream_t st);
 template <typename T>
 int warp_fwd_ndhwc(const T* x1, const T* x2, int64_t sB, const float* flow, const float* xs, const float* ys,
                    T* out, int B, int C, int H, int W, cudaStream_t st);

@@ -14,8 +14,8 @@ from smow_net_b200 import _lib, ops
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-FWD_VARIANTS = [0, 1]
-BWD_VARIANTS = [0, 1]
+FWD_VARIANTS = [0, 1, 2]
+BWD_VARIANTS = [0, 1, 2]
 
 
 def _scale(t):
@@ -105,7 +105,7 @@ def test_warp_bf16_storage(fv, bv, variants):
     want = torch_ref.warp_with_grads(x.float(), flow, gout.float())
     assert got[0].dtype == torch.bfloat16 and got[1].dtype == torch.bfloat16 and got[2].dtype == torch.float32
     assert float((got[0].float() - want[0]).abs().max()) <= 2e-2
-    if bv == 1:  # variant 0 accumulates the scatter in bf16 atomics; the tiled kernel accumulates in fp32
+    if bv >= 1:  # variant 0 accumulates the scatter in bf16 atomics; the tiled kernels accumulate in fp32
         assert float((got[1].float() - want[1]).abs().max()) <= 2e-2 * _scale(want[1])
     assert float((got[2] - want[2]).abs().max()) <= 1e-4 * _scale(want[2])
 
@@ -169,9 +169,10 @@ def test_warp_backward_converging_and_far_flows(bv, variants):
     check_warp(run_warp(x, flow, gout), torch_ref.warp_with_grads(x, flow, gout), tol=2e-5)
 
 
-def test_warp_backward_is_deterministic(variants):
-    """The tiled backward sums in a fixed order (ATen's atomics do not)."""
-    _lib.set_option("warp_bwd_variant", 1)
+@pytest.mark.parametrize("bv", [1, 2])
+def test_warp_backward_is_deterministic(bv, variants):
+    """The tiled backward kernels sum in a fixed order (ATen's atomics do not)."""
+    _lib.set_option("warp_bwd_variant", bv)
     g = torch.Generator(device=DEV).manual_seed(4)
     x = torch.randn(4, 32, 2, 128, 128, device=DEV, generator=g)
     flow = torch.randn(4, 2, 2, 128, 128, device=DEV, generator=g) * 0.8
