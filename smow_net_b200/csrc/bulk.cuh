@@ -55,6 +55,11 @@ __device__ __forceinline__ void bulk_wait_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// asynchronous L2 prefetch of a contiguous global range (bytes % 16 == 0, 16 B aligned): no
+// registers, no shared memory; a later ld.global of the range is an L2 hit
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (needed before bulk_s2g of data written with st.shared)
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -14,12 +14,14 @@
 // Tiling, the inverse-gather backward, the register gather lists, the near/far predicate and
 // the far-contribution side kernel are those of warp_stack_bwd_tiled.cu.
 #include "warp_stack_tiled.cuh"
+#include "bulk.cuh"
 
 namespace smow {
 
 constexpr int CV_THREADS = 512;
 constexpr int CV_NP = 2;   // pixels per thread
 constexpr int CV_K = 6;    // register gather-list length (bilinear scatter: 4 sources per target on average)
+constexpr int CV_PF = 3;   // L2 prefetch distance, in channel chunks
 
 struct CvGeom { int R, HALO, DCAP, WR, U, nbands, ntiles; };
 
@@ -81,6 +83,23 @@ warp_fwd_cvec_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
     wr0 = ti.h0 - g.HALO;
     return (ti.t ? x2 : x1) + ti.b * sB + (int64_t)(ch * 4) * sC;
   };
+  // L2 prefetch of pipeline iteration `it` (lanes 0..3 of warp 0: one channel plane each) and, at a
+  // tile boundary, of the tile's flow rows: DRAM latency is taken off the register-staged fill
+  auto prefetch = [&](int it) {
+    if (it >= total_it || tid >= 8) return;
+    const int tl = it / nchunk, ch = it - tl * nchunk;
+    const TileId tj = tile_of(blockIdx.x + tl * gridDim.x, g);
+    const int r_lo = max(0, tj.h0 - g.HALO), r_hi = min(H, tj.h0 + g.R + g.HALO);
+    if (tid < 4) {
+      const float* p = (tj.t ? x2 : x1) + tj.b * sB + (int64_t)(ch * 4 + tid) * sC + r_lo * W;
+      bulk_prefetch_l2(p, (uint32_t)((r_hi - r_lo) * W * sizeof(float)));
+    } else if (ch == 0 && tid < 6) {
+      const int h1 = min(H, tj.h0 + g.R);
+      const float* p = flow + ((int64_t)(tj.b * 2 + (tid - 4)) * 2 + tj.t) * HW + tj.h0 * W;
+      bulk_prefetch_l2(p, (uint32_t)((h1 - tj.h0) * W * sizeof(float)));
+    }
+  };
+  for (int d = 1; d <= CV_PF; ++d) prefetch(d);
   {  // prologue: chunk 0 -> buffer 0
     Unit v;
     int wr0;
@@ -127,7 +146,8 @@ warp_fwd_cvec_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
         }
       }
     }
-    // prefetch the next chunk into registers
+    prefetch(it + 1 + CV_PF);
+    // stage the next chunk in registers
     Unit nxt;
     bool have_nxt = false;
     if (it + 1 < total_it) {
@@ -214,6 +234,26 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
     ok = load_unit(vx, xsrc, sC, tid, g, W, H, ti.h0 - g.HALO);
     if (ok) load_unit(vg, gsrc, (int64_t)4 * HW, tid, g, W, H, ti.h0 - g.HALO);
   };
+  auto prefetch = [&](int it) {   // lanes 0..11: x window, gout window, gout pass rows; 12..13: flow rows
+    if (it >= total_it || tid >= 14) return;
+    const int tl = it / nchunk, ch = it - tl * nchunk;
+    const TileId tj = tile_of(blockIdx.x + tl * gridDim.x, g);
+    const int r_lo = max(0, tj.h0 - g.HALO), r_hi = min(H, tj.h0 + g.R + g.HALO);
+    const int h1 = min(H, tj.h0 + g.R);
+    const uint32_t wbytes = (uint32_t)((r_hi - r_lo) * W * sizeof(float));
+    const int c = ch * 4 + (tid & 3);
+    if (tid < 4) {
+      bulk_prefetch_l2((tj.t ? x2 : x1) + tj.b * sB + (int64_t)c * sC + r_lo * W, wbytes);
+    } else if (tid < 8) {
+      bulk_prefetch_l2(gout + ((int64_t)(tj.b * C + c) * 4 + 1 + tj.t) * HW + r_lo * W, wbytes);
+    } else if (tid < 12) {
+      bulk_prefetch_l2(gout + ((int64_t)(tj.b * C + c) * 4 + (tj.t ? 3 : 0)) * HW + tj.h0 * W,
+                       (uint32_t)((h1 - tj.h0) * W * sizeof(float)));
+    } else if (ch == 0) {
+      bulk_prefetch_l2(flow + ((int64_t)(tj.b * 2 + (tid - 12)) * 2 + tj.t) * HW + r_lo * W, wbytes);
+    }
+  };
+  for (int d = 1; d <= CV_PF; ++d) prefetch(d);
   {
     Unit vx, vg;
     bool ok = false;
@@ -319,6 +359,7 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
       }
     }
     // ---------------- phase 2: one chunk of 4 channels ----------------
+    prefetch(it + 1 + CV_PF);
     Unit nx, ng;
     bool have_nxt = false;
     if (it + 1 < total_it) fetch(it + 1, nx, ng, have_nxt);
