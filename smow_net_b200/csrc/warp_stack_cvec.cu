@@ -209,11 +209,29 @@ warp_fwd_cvec_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
 // ------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------
+constexpr int CV_KO = 4;   // extra gather-list entries per target kept in shared memory (beyond CV_K)
+
 __device__ __forceinline__ bool cv_near_row(int sy, int ty, const CvGeom& g) {
   const int h0 = (ty / g.R) * g.R;
   return sy >= h0 - g.HALO && sy < h0 + g.R + g.HALO;
 }
 __device__ __forceinline__ bool cv_near_col(int dx, const CvGeom& g) { return dx >= -g.DCAP && dx <= g.DCAP; }
+
+// axis_coord with the division by a power-of-two size done as an exact multiplication
+__device__ __forceinline__ Axis axis_coord_fast(float base, float flow, int size, float inv, bool pow2) {
+  if (!pow2) return axis_coord(base, flow, size);
+  float gq = __fadd_rn(base, __fmul_rn(flow, inv));       // flow / 2^k == flow * 2^-k exactly
+  const bool pass_clamp = (gq >= -1.f) && (gq <= 1.f);
+  gq = fminf(fmaxf(gq, -1.f), 1.f);
+  const float hi = (float)(size - 1);
+  float i = __fmul_rn(__fmul_rn(__fadd_rn(gq, 1.f), 0.5f), hi);
+  const bool pass_clip = (i > 0.f) && (i < hi);
+  i = fminf(hi, fmaxf(i, 0.f));
+  Axis a;
+  a.i = i; a.i0f = floorf(i); a.i0 = (int)a.i0f;
+  a.gmult = (pass_clamp && pass_clip) ? 1.f : 0.f;
+  return a;
+}
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
 warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
@@ -223,14 +241,21 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int HW = H * W;
   const int slots = g.WR * W;
-  float4* base4 = reinterpret_cast<float4*>(smem_raw);
-  // [buffer 0: x window | gout window][buffer 1: x | gout][ix][iy][range]
-  float* s_ix = reinterpret_cast<float*>(base4 + 4 * slots);
+  const uint32_t buf_bytes = (uint32_t)(2 * slots * sizeof(float4));   // one stage: x window | gout window
+  const uint32_t g_off = (uint32_t)(slots * sizeof(float4));
+  // [stage 0][stage 1][ix][iy][anchor][overflow weights][overflow offsets][gates][range]
+  float* s_ix = reinterpret_cast<float*>(smem_raw + 2 * buf_bytes);
   float* s_iy = s_ix + slots;
-  int* s_rng = reinterpret_cast<int*>(s_iy + slots);
+  int* s_an = reinterpret_cast<int*>(s_iy + slots);                    // (y0 << 16) | x0 of every window pixel
+  float* s_ovw = reinterpret_cast<float*>(s_an + slots);               // [CV_KO][CV_NP][CV_THREADS]
+  int* s_ovo = reinterpret_cast<int*>(s_ovw + CV_KO * CV_NP * CV_THREADS);
+  int* s_rng = s_ovo + CV_KO * CV_NP * CV_THREADS;
+  unsigned char* s_gate = reinterpret_cast<unsigned char*>(s_rng + 4);  // core pixels: bit0 = x gate, bit1 = y gate
   const int tid = threadIdx.x;
   const int nchunk = C >> 2;
   const int64_t cs = (int64_t)4 * HW;
+  const bool w_pow2 = (W & (W - 1)) == 0, h_pow2 = (H & (H - 1)) == 0;
+  const float inv_w = 1.f / (float)W, inv_h = 1.f / (float)H;
   const int u_p4 = 4 * tid;
   const int u_row = u_p4 / W, u_col = u_p4 - u_row * W;
   const bool u_any = tid < g.U;
@@ -273,13 +298,14 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
       Unit vx, vg;
       load_unit(vx, x_ptr(ti, 0), sC);
       load_unit(vg, g_ptr(ti, 0), cs);
-      store_unit(base4, u_p4, vx);
-      store_unit(base4 + slots, u_p4, vg);
+      store_unit(reinterpret_cast<float4*>(smem_raw), u_p4, vx);
+      store_unit(reinterpret_cast<float4*>(smem_raw + g_off), u_p4, vg);
     }
   }
   __syncthreads();
 
-  int parity = 0;
+  unsigned char* cur = smem_raw;                 // stage being consumed
+  unsigned char* oth = smem_raw + buf_bytes;     // stage being filled
   for (; tile < g.ntiles; tile += gridDim.x) {
     const int ntile = tile + gridDim.x;
     const bool has_next_tile = ntile < g.ntiles;
@@ -287,20 +313,22 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
     const int wr0 = ti.h0 - g.HALO;
     const int wlo = max(0, wr0), whi = min(H, ti.h0 + g.R + g.HALO);
     const float* fl = flow + ((int64_t)(ti.b * 2) * 2 + ti.t) * HW;
-    // ---------------- phase 0: window sample coordinates + displacement range ----------------
+    // ---------------- phase 0: sample coordinates of the window + displacement range ----------------
     if (tid < 4) s_rng[tid] = (tid & 1) ? -(1 << 30) : (1 << 30);
     __syncthreads();
     {
       int mn_x = 1 << 30, mx_x = -(1 << 30), mn_y = 1 << 30, mx_y = -(1 << 30);
-      int r = tid / W, col = tid - r * W;             // CV_THREADS may exceed W: advance (r, col) incrementally
+      int r = tid / W, col = tid - r * W;
       const int dr = CV_THREADS / W, dc = CV_THREADS - dr * W;
       for (int i = tid; i < slots; i += CV_THREADS) {
         const int sy = wr0 + r;
         if (sy >= wlo && sy < whi) {
           const int p = sy * W + col;
-          const Axis ax = axis_coord(__ldg(xs + col), __ldg(fl + p), W);
-          const Axis ay = axis_coord(__ldg(ys + sy), __ldg(fl + p + 2 * (int64_t)HW), H);
-          s_ix[i] = ax.i; s_iy[i] = ay.i;
+          const Axis ax = axis_coord_fast(__ldg(xs + col), __ldg(fl + p), W, inv_w, w_pow2);
+          const Axis ay = axis_coord_fast(__ldg(ys + sy), __ldg(fl + p + 2 * (int64_t)HW), H, inv_h, h_pow2);
+          s_ix[i] = ax.i; s_iy[i] = ay.i; s_an[i] = (ay.i0 << 16) | ax.i0;
+          const int cr = r - g.HALO;
+          if (cr >= 0 && cr < g.R) s_gate[cr * W + col] = (unsigned char)((ax.gmult != 0.f ? 1 : 0) | (ay.gmult != 0.f ? 2 : 0));
           const int dx = ax.i0 - col, dy = ay.i0 - sy;
           mn_x = min(mn_x, dx); mx_x = max(mx_x, dx); mn_y = min(mn_y, dy); mx_y = max(mx_y, dy);
         }
@@ -318,7 +346,7 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
     const int dxlo = max(s_rng[0], -g.DCAP), dxhi = min(s_rng[1], g.DCAP);
     const int dylo = s_rng[2], dyhi = s_rng[3];
 
-    // visit every source of target (ty,tx) in fixed order: f(weight, swizzled slot, hit index)
+    // visit every source of target (ty,tx) in fixed order: f(weight, byte offset of the source slot, hit index)
     auto probe = [&](int ty, int tx, auto&& f) {
       int n = 0;
       const int sy_a = max(wlo, ty - 1 - dyhi), sy_b = min(whi - 1, ty - dylo);
@@ -326,15 +354,16 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
       for (int sy = sy_a; sy <= sy_b; ++sy) {
         const int rowo = (sy - wr0) * W;
         for (int sx = sx_a; sx <= sx_b; ++sx) {
-          const float ix = s_ix[rowo + sx], iy = s_iy[rowo + sx];
-          const float x0f = floorf(ix), y0f = floorf(iy);
-          const int x0 = (int)x0f, y0 = (int)y0f;
+          const int an = s_an[rowo + sx];
+          const int x0 = an & 0xffff, y0 = an >> 16;
           const int ex = tx - x0, ey = ty - y0;
           if ((unsigned)ex > 1u || (unsigned)ey > 1u) continue;
           if (!cv_near_col(x0 - sx, g)) continue;
+          const float ix = s_ix[rowo + sx], iy = s_iy[rowo + sx];
+          const float x0f = (float)x0, y0f = (float)y0;
           const float wx = ex ? __fsub_rn(ix, x0f) : __fsub_rn(__fadd_rn(x0f, 1.f), ix);
           const float wy = ey ? __fsub_rn(iy, y0f) : __fsub_rn(__fadd_rn(y0f, 1.f), iy);
-          f(__fmul_rn(wx, wy), swz(rowo + sx), n);
+          f(__fmul_rn(wx, wy), swz(rowo + sx) * 16, n);
           ++n;
         }
       }
@@ -343,37 +372,46 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
 
     // ---------------- phase 1: gather lists (targets) and footprints (sources) ----------------
     float lw[CV_NP][CV_K];
-    int lo[CV_NP][CV_K];
-    int ln[CV_NP], tpix[CV_NP], s_own[CV_NP];
-    float wx0[CV_NP], wx1[CV_NP], wy0[CV_NP], wy1[CV_NP], gate_x[CV_NP], gate_y[CV_NP];
+    int lo[CV_NP][CV_K];                 // byte offsets of the gather sources inside a window buffer
+    int ln[CV_NP], tpix[CV_NP], o_own[CV_NP];
+    float wx0[CV_NP], wx1[CV_NP], wy0[CV_NP], wy1[CV_NP];
     float2 gixp[CV_NP], giyp[CV_NP];
-    int s_nw[CV_NP], s_ne[CV_NP], s_sw[CV_NP], s_se[CV_NP], gofs[CV_NP];
+    int o_nw[CV_NP], o_ne[CV_NP], o_sw[CV_NP], o_se[CV_NP], gofs[CV_NP];
 #pragma unroll
     for (int k = 0; k < CV_NP; ++k) {
       const int h = ti.h0 + p_r[k];
+      const int ownp = (p_r[k] + g.HALO) * W + p_c[k];
       gixp[k] = giyp[k] = f2(0.f, 0.f);
-      s_own[k] = swz((p_r[k] + g.HALO) * W + p_c[k]);
+      o_own[k] = swz(ownp) * 16;
 #pragma unroll
-      for (int j = 0; j < CV_K; ++j) { lw[k][j] = 0.f; lo[k][j] = s_own[k]; }
-      tpix[k] = -1; ln[k] = 0; s_nw[k] = -1; s_ne[k] = s_sw[k] = s_se[k] = 0; gofs[k] = 0;
-      wx0[k] = wx1[k] = wy0[k] = wy1[k] = gate_x[k] = gate_y[k] = 0.f;
+      for (int j = 0; j < CV_K; ++j) { lw[k][j] = 0.f; lo[k][j] = o_own[k]; }
+      tpix[k] = -1; ln[k] = 0; o_nw[k] = -1; o_ne[k] = o_sw[k] = o_se[k] = 0; gofs[k] = 0;
+      wx0[k] = wx1[k] = wy0[k] = wy1[k] = 0.f;
       if (p_r[k] < g.R && h < H) {
         tpix[k] = h * W + p_c[k];
-        ln[k] = probe(h, p_c[k], [&](float w, int slot, int n) {
+        ln[k] = probe(h, p_c[k], [&](float w, int off, int n) {
 #pragma unroll
           for (int j = 0; j < CV_K; ++j)
-            if (n == j) { lw[k][j] = w; lo[k][j] = slot; }
+            if (n == j) { lw[k][j] = w; lo[k][j] = off; }
+          if (n >= CV_K && n < CV_K + CV_KO) {
+            s_ovw[((n - CV_K) * CV_NP + k) * CV_THREADS + tid] = w;
+            s_ovo[((n - CV_K) * CV_NP + k) * CV_THREADS + tid] = off;
+          }
         });
-        const int p = tpix[k];
-        const Footprint fp = footprint(__ldg(xs + p_c[k]), __ldg(ys + h), __ldg(fl + p), __ldg(fl + p + 2 * (int64_t)HW), W, H);
-        wx0[k] = fp.wx0; wx1[k] = fp.wx1; wy0[k] = fp.wy0; wy1[k] = fp.wy1;
-        gate_x[k] = fp.gx_gate; gate_y[k] = fp.gy_gate;
-        gofs[k] = (fp.y0 * W + fp.x0) * 4 + (fp.x1ok ? 1 : 0) + (fp.y1ok ? 2 : 0);
-        const int sr = fp.y0 - wr0;
-        const int dx = fp.x1ok ? 1 : 0, dy = fp.y1ok ? W : 0;
-        if (sr >= 0 && sr + (fp.y1ok ? 1 : 0) < g.WR) {
-          const int q = sr * W + fp.x0;
-          s_nw[k] = swz(q); s_ne[k] = swz(q + dx); s_sw[k] = swz(q + dy); s_se[k] = swz(q + dy + dx);
+        // own pixel as a source: footprint from the phase-0 tables
+        const float ix = s_ix[ownp], iy = s_iy[ownp];
+        const int an = s_an[ownp];
+        const int x0 = an & 0xffff, y0 = an >> 16;
+        const float x0f = (float)x0, y0f = (float)y0;
+        wx0[k] = __fsub_rn(__fadd_rn(x0f, 1.f), ix); wx1[k] = __fsub_rn(ix, x0f);
+        wy0[k] = __fsub_rn(__fadd_rn(y0f, 1.f), iy); wy1[k] = __fsub_rn(iy, y0f);
+        const bool x1ok = x0 + 1 <= W - 1, y1ok = y0 + 1 <= H - 1;
+        gofs[k] = (y0 * W + x0) * 4 + (x1ok ? 1 : 0) + (y1ok ? 2 : 0);
+        const int sr = y0 - wr0;
+        const int dx = x1ok ? 1 : 0, dy = y1ok ? W : 0;
+        if (sr >= 0 && sr + (y1ok ? 1 : 0) < g.WR) {
+          const int q = sr * W + x0;
+          o_nw[k] = swz(q) * 16; o_ne[k] = swz(q + dx) * 16; o_sw[k] = swz(q + dy) * 16; o_se[k] = swz(q + dy + dx) * 16;
         }
       }
     }
@@ -401,46 +439,55 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
         have_nxt = ok_next;
         if (have_nxt) { load_unit(nx, x_ptr(tn, 0), sC); load_unit(ng, g_ptr(tn, 0), cs); }
       }
-      const float4* X = base4 + (size_t)parity * 2 * slots;
-      const float4* G = X + slots;
+      const unsigned char* Xb = cur;
+      const unsigned char* Gb = cur + g_off;
 #pragma unroll
       for (int k = 0; k < CV_NP; ++k) {
         if (tpix[k] < 0) continue;
-        const float* gp = gpass + (int64_t)(ch * 4) * cs + tpix[k];
+        const float* gp = gpass + tpix[k];
         const float p0 = __ldg(gp), p1 = __ldg(gp + cs), p2 = __ldg(gp + 2 * cs), p3 = __ldg(gp + 3 * cs);
         // target side: gather the scatter (zero-weight padding instead of predicates)
         float2 a01 = f2(0.f, 0.f), a23 = f2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < CV_K; ++j) {
-          const float4 v = G[lo[k][j]];
+          const float4 v = *reinterpret_cast<const float4*>(Gb + lo[k][j]);
           a01 = __ffma2_rn(bc(lw[k][j]), f2(v.x, v.y), a01);
           a23 = __ffma2_rn(bc(lw[k][j]), f2(v.z, v.w), a23);
         }
-        if (ln[k] > CV_K) {
-          const int h = ti.h0 + p_r[k];
-          probe(h, p_c[k], [&](float w, int slot, int n) {
-            if (n >= CV_K) {
-              const float4 v = G[slot];
-              a01 = __ffma2_rn(bc(w), f2(v.x, v.y), a01);
-              a23 = __ffma2_rn(bc(w), f2(v.z, v.w), a23);
-            }
-          });
+        if (ln[k] > CV_K) {                       // rare: entries CV_K .. CV_K+CV_KO-1 live in shared memory
+          const int ne = min(ln[k], CV_K + CV_KO) - CV_K;
+          for (int j = 0; j < ne; ++j) {
+            const float w = s_ovw[(j * CV_NP + k) * CV_THREADS + tid];
+            const float4 v = *reinterpret_cast<const float4*>(Gb + s_ovo[(j * CV_NP + k) * CV_THREADS + tid]);
+            a01 = __ffma2_rn(bc(w), f2(v.x, v.y), a01);
+            a23 = __ffma2_rn(bc(w), f2(v.z, v.w), a23);
+          }
+          if (ln[k] > CV_K + CV_KO) {             // very rare: strongly converging flow, re-probe
+            probe(ti.h0 + p_r[k], p_c[k], [&](float w, int off, int n) {
+              if (n >= CV_K + CV_KO) {
+                const float4 v = *reinterpret_cast<const float4*>(Gb + off);
+                a01 = __ffma2_rn(bc(w), f2(v.x, v.y), a01);
+                a23 = __ffma2_rn(bc(w), f2(v.z, v.w), a23);
+              }
+            });
+          }
         }
         // source side: flow-gradient sums, factored:  gix += go * (wy0 (ne-nw) + wy1 (se-sw)),
         //                                             giy += go * (wx0 (sw-nw) + wx1 (se-ne))
         // (an out-of-bounds tap aliases an in-bounds slot; its weight wx1 / wy1 is exactly 0 there and the
         // other axis is gated off, so the sums equal ATen's skip-the-tap form)
-        const float4 go = G[s_own[k]];
+        const float4 go = *reinterpret_cast<const float4*>(Gb + o_own[k]);
         float4 vnw, vne, vsw, vse;
-        if (s_nw[k] >= 0) {
-          vnw = X[s_nw[k]]; vne = X[s_ne[k]]; vsw = X[s_sw[k]]; vse = X[s_se[k]];
+        if (o_nw[k] >= 0) {
+          vnw = *reinterpret_cast<const float4*>(Xb + o_nw[k]); vne = *reinterpret_cast<const float4*>(Xb + o_ne[k]);
+          vsw = *reinterpret_cast<const float4*>(Xb + o_sw[k]); vse = *reinterpret_cast<const float4*>(Xb + o_se[k]);
         } else {
           const bool x1ok = gofs[k] & 1, y1ok = gofs[k] & 2;
           const int o = gofs[k] >> 2, dx = x1ok ? 1 : 0, dy = y1ok ? W : 0;
           float t[4][4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float* q = xg + (int64_t)(ch * 4 + c) * sC + o;
+            const float* q = xg + c * sC + o;
             t[0][c] = __ldg(q); t[1][c] = __ldg(q + dx); t[2][c] = __ldg(q + dy); t[3][c] = __ldg(q + dy + dx);
           }
           vnw = make_float4(t[0][0], t[0][1], t[0][2], t[0][3]); vne = make_float4(t[1][0], t[1][1], t[1][2], t[1][3]);
@@ -458,25 +505,26 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
           gixp[k] = __ffma2_rn(gh, tx, gixp[k]);
           giyp[k] = __ffma2_rn(gh, ty, giyp[k]);
         }
-        float* o = gxo + (int64_t)(ch * 4) * sC + tpix[k];
+        float* o = gxo + tpix[k];
         o[0] = __fadd_rn(p0, a01.x); o[sC] = __fadd_rn(p1, a01.y);
         o[2 * sC] = __fadd_rn(p2, a23.x); o[3 * sC] = __fadd_rn(p3, a23.y);
       }
+      gpass += 4 * cs; gxo += 4 * sC; xg += 4 * sC;
       if (have_nxt) {
-        float4* nb = base4 + (size_t)(parity ^ 1) * 2 * slots;
-        store_unit(nb, u_p4, nx);
-        store_unit(nb + slots, u_p4, ng);
+        store_unit(reinterpret_cast<float4*>(oth), u_p4, nx);
+        store_unit(reinterpret_cast<float4*>(oth + g_off), u_p4, ng);
       }
-      parity ^= 1;
+      unsigned char* tmp = cur; cur = oth; oth = tmp;
       __syncthreads();
     }
     // ---------------- phase 3: flow gradient of this tile ----------------
 #pragma unroll
     for (int k = 0; k < CV_NP; ++k) {
       if (tpix[k] < 0) continue;
+      const int gate = s_gate[p_r[k] * W + p_c[k]];
       const int64_t fo = ((int64_t)(ti.b * 2) * 2 + ti.t) * HW + tpix[k];
-      const float mx = __fmul_rn(gate_x[k], __fmul_rn((float)(W - 1), 0.5f));
-      const float my = __fmul_rn(gate_y[k], __fmul_rn((float)(H - 1), 0.5f));
+      const float mx = __fmul_rn((gate & 1) ? 1.f : 0.f, __fmul_rn((float)(W - 1), 0.5f));
+      const float my = __fmul_rn((gate & 2) ? 1.f : 0.f, __fmul_rn((float)(H - 1), 0.5f));
       gflow[fo] = __fdiv_rn(__fmul_rn(mx, __fadd_rn(gixp[k].x, gixp[k].y)), (float)W);
       gflow[fo + 2 * (int64_t)HW] = __fdiv_rn(__fmul_rn(my, __fadd_rn(giyp[k].x, giyp[k].y)), (float)H);
     }
@@ -567,7 +615,8 @@ int warp_bwd_cvec(const float* gout, const float* x1, const float* x2, int64_t s
                   int W, cudaStream_t st) {
   CvGeom g;
   if (!cv_geometry(g, B, H, W, option(OPT_BWD_HALO))) return SMOW_ERANGE;
-  const size_t smem = 4 * (size_t)g.WR * W * sizeof(float4) + 2 * (size_t)g.WR * W * sizeof(float) + 4 * sizeof(int);
+  const size_t smem = 4 * (size_t)g.WR * W * sizeof(float4) + 3 * (size_t)g.WR * W * sizeof(float) +
+                      2 * (size_t)CV_KO * CV_NP * CV_THREADS * sizeof(float) + 4 * sizeof(int) + (size_t)g.R * W;
   static thread_local size_t configured = 0;
   if (int e = cv_prepare(warp_bwd_cvec_kernel, smem, configured)) return e;
   const int sms = device_info().sms;
