@@ -158,8 +158,11 @@ static int fwd_impl(const T* x1, const T* x2, int64_t sB, int64_t sC, const floa
                     const float* xs, const float* ys, T* out, int B, int C, int H, int W,
                     int layout, cudaStream_t st) {
   if (layout == SMOW_NDHWC) return warp_fwd_ndhwc<T>(x1, x2, sB, flow, xs, ys, out, B, C, H, W, st);
-  const int variant = option(OPT_WARP_FWD_VARIANT);
-  if (variant < 0 || variant > 2) return fail(SMOW_EINVAL, "unknown warp_fwd_variant %d", variant);
+  int variant = option(OPT_WARP_FWD_VARIANT);
+  if (variant < -1 || variant > 2) return fail(SMOW_EINVAL, "unknown warp_fwd_variant %d", variant);
+  // auto (-1), from the r1 sweep (profiles/r1_sweep.md): the bulk-copy staged planes win for few
+  // channels, the channel-vectorised tiles from 64 channels up
+  if (variant == -1) variant = (std::is_same<T, float>::value && C >= 64) ? 2 : 1;
   // the tile kernels need whole 16 B rows; odd shapes take the direct kernel (same results)
   const bool tile_ok = tiled_shape_ok<T>(x1, x2, out, sB, sC, C, H, W);
   if constexpr (std::is_same<T, float>::value) {
@@ -183,7 +186,9 @@ static int bwd_impl(const T* gout, const T* x1, const T* x2, int64_t sB, int64_t
                     int layout, cudaStream_t st) {
   if (layout == SMOW_NDHWC)
     return warp_bwd_ndhwc<T>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, st);
-  const int variant = option(OPT_WARP_BWD_VARIANT);
+  int variant = option(OPT_WARP_BWD_VARIANT);
+  if (variant < -1 || variant > 2) return fail(SMOW_EINVAL, "unknown warp_bwd_variant %d", variant);
+  if (variant == -1) variant = 2;   // falls through to 1 for bf16 / uncovered shapes, then to 0
   const bool tile_ok = tiled_shape_ok<T>(x1, x2, gout, sB, sC, C, H, W) && aligned16(gx1) && aligned16(gx2);
   if constexpr (std::is_same<T, float>::value) {
     if (variant == 2 && tile_ok) {
@@ -195,7 +200,6 @@ static int bwd_impl(const T* gout, const T* x1, const T* x2, int64_t sB, int64_t
     const int rc = warp_bwd_tiled<T>(gout, x1, x2, sB, sC, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, st);
     if (rc != SMOW_ERANGE) return rc;   // rows too wide for one tile: the scatter kernel below handles them
   }
-  if (variant < 0 || variant > 2) return fail(SMOW_EINVAL, "unknown warp_bwd_variant %d", variant);
   if ((int64_t)B * C > 65535) return fail(SMOW_ERANGE, "B*C too large for variant 0");
   Frames<const T> x{x1, x2, sB, sC};
   Frames<T> gx{gx1, gx2, sB, sC};

@@ -21,7 +21,8 @@
 
 namespace smow {
 
-constexpr int CV_THREADS = 512;
+constexpr int CV_THREADS = 256;
+constexpr int CV_CTAS = 2;    // resident CTAs per SM the kernels are sized for
 constexpr int CV_NP = 2;   // pixels per thread
 constexpr int CV_K = 6;    // register gather-list length (bilinear scatter: 4 sources per target on average)
 constexpr int CV_PF = 3;   // L2 prefetch distance, in channel chunks
@@ -60,7 +61,7 @@ __device__ __forceinline__ TileId tile_of(int tile, const CvGeom& g) {
 // ------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CV_THREADS, 1)
+__global__ void __launch_bounds__(CV_THREADS, CV_CTAS)
 warp_fwd_cvec_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int64_t sB, int64_t sC,
                      const float* __restrict__ flow, const float* __restrict__ xs, const float* __restrict__ ys,
                      float* __restrict__ out, int C, int H, int W, CvGeom g) {
@@ -233,7 +234,7 @@ __device__ __forceinline__ Axis axis_coord_fast(float base, float flow, int size
   return a;
 }
 
-__global__ void __launch_bounds__(CV_THREADS, 1)
+__global__ void __launch_bounds__(CV_THREADS, CV_CTAS)
 warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
                      int64_t sB, int64_t sC, const float* __restrict__ flow, const float* __restrict__ xs,
                      const float* __restrict__ ys, float* __restrict__ gx1, float* __restrict__ gx2,
@@ -570,16 +571,17 @@ warp_bwd_cvec_far_kernel(const float* __restrict__ gout, const float* __restrict
 // host
 // ------------------------------------------------------------------------------
 static bool cv_geometry(CvGeom& g, int B, int H, int W, int halo) {
-  g.HALO = halo < 1 ? 1 : halo;
-  g.DCAP = g.HALO + 1;
   int R = (CV_THREADS * CV_NP) / W;
   if (R < 1) return false;
   if (R > H) R = H;
   g.R = R;
+  g.HALO = halo < 1 ? 1 : halo;
+  while (g.HALO > 1 && (R + 2 * g.HALO) * W / 4 > CV_THREADS) --g.HALO;   // one fill unit per thread per array
+  g.DCAP = g.HALO + 1;
   g.WR = R + 2 * g.HALO;
   if ((g.WR * W) % 8 != 0) return false;
   g.U = g.WR * W / 4;
-  if (g.U > CV_THREADS) return false;          // one fill unit per thread per array
+  if (g.U > CV_THREADS) return false;
   g.nbands = (H + R - 1) / R;
   g.ntiles = 2 * B * g.nbands;
   return true;
@@ -603,7 +605,7 @@ int warp_fwd_cvec(const float* x1, const float* x2, int64_t sB, int64_t sC, cons
   const size_t smem = 2 * (size_t)g.WR * W * sizeof(float4);
   static thread_local size_t configured = 0;
   if (int e = cv_prepare(warp_fwd_cvec_kernel, smem, configured)) return e;
-  const int sms = device_info().sms;
+  const int sms = device_info().sms * CV_CTAS;
   const int grid = g.ntiles < sms ? g.ntiles : sms;
   warp_fwd_cvec_kernel<<<grid, CV_THREADS, smem, st>>>(x1, x2, sB, sC, flow, xs, ys, out, C, H, W, g);
   count_launch();
@@ -619,7 +621,7 @@ int warp_bwd_cvec(const float* gout, const float* x1, const float* x2, int64_t s
                       2 * (size_t)CV_KO * CV_NP * CV_THREADS * sizeof(float) + 4 * sizeof(int) + (size_t)g.R * W;
   static thread_local size_t configured = 0;
   if (int e = cv_prepare(warp_bwd_cvec_kernel, smem, configured)) return e;
-  const int sms = device_info().sms;
+  const int sms = device_info().sms * CV_CTAS;
   const int grid = g.ntiles < sms ? g.ntiles : sms;
   warp_bwd_cvec_kernel<<<grid, CV_THREADS, smem, st>>>(gout, x1, x2, sB, sC, flow, xs, ys, gx1, gx2, gflow, C, H, W, g);
   warp_bwd_cvec_far_kernel<<<dim3((H * W + 255) / 256, 2 * B), 256, 0, st>>>(gout, flow, xs, ys, gx1, gx2, sB, sC, C,
