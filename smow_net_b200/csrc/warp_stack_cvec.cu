@@ -210,7 +210,7 @@ warp_fwd_cvec_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
 // ------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------
-constexpr int CV_KO = 4;   // extra gather-list entries per target kept in shared memory (beyond CV_K)
+constexpr int CV_KO = 2;   // extra gather-list entries per target kept in shared memory (beyond CV_K)
 
 __device__ __forceinline__ bool cv_near_row(int sy, int ty, const CvGeom& g) {
   const int h0 = (ty / g.R) * g.R;
@@ -251,7 +251,9 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
   float* s_ovw = reinterpret_cast<float*>(s_an + slots);               // [CV_KO][CV_NP][CV_THREADS]
   int* s_ovo = reinterpret_cast<int*>(s_ovw + CV_KO * CV_NP * CV_THREADS);
   int* s_rng = s_ovo + CV_KO * CV_NP * CV_THREADS;
-  unsigned char* s_gate = reinterpret_cast<unsigned char*>(s_rng + 4);  // core pixels: bit0 = x gate, bit1 = y gate
+  float* s_pass = reinterpret_cast<float*>(s_rng + 4);                  // [2 stages][4 channels][R*W], cp.async filled
+  float* s_flow = s_pass + 2 * 4 * g.R * W;                             // [2 components][WR*W] of the tile being prepared
+  unsigned char* s_gate = reinterpret_cast<unsigned char*>(s_flow + 2 * slots);  // core pixels: bit0 = x gate, bit1 = y gate
   const int tid = threadIdx.x;
   const int nchunk = C >> 2;
   const int64_t cs = (int64_t)4 * HW;
@@ -292,7 +294,28 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
       bulk_prefetch_l2(flow + ((int64_t)(t.b * 2 + (tid - 12)) * 2 + t.t) * HW + r_lo * W, wbytes);
     }
   };
+  // cp.async (16 B, no registers): gout pass-slot rows of one chunk -> s_pass[stage]; flow rows of a tile -> s_flow
+  const int core = g.R * W;
+  auto copy_pass = [&](const TileId& t, int ch, int stage) {
+    const int rows = min(g.R, H - t.h0);
+    const int upc = rows * W / 4;                                 // 16-byte units per channel
+    const float* src = gout + ((int64_t)(t.b * C + ch * 4) * 4 + (t.t ? 3 : 0)) * HW + t.h0 * W;
+    float* dst = s_pass + stage * 4 * core;
+    for (int c = 0; c < 4; ++c)
+      for (int j = tid; j < upc; j += CV_THREADS) cp_async16(dst + c * core + 4 * j, src + c * cs + 4 * j);
+  };
+  auto copy_flow = [&](const TileId& t) {
+    const int r_lo = max(0, t.h0 - g.HALO), r_hi = min(H, t.h0 + g.R + g.HALO);
+    const int units = (r_hi - r_lo) * W / 4, woff = (r_lo - (t.h0 - g.HALO)) * W;
+    for (int comp = 0; comp < 2; ++comp) {
+      const float* src = flow + ((int64_t)(t.b * 2 + comp) * 2 + t.t) * HW + r_lo * W;
+      for (int j = tid; j < units; j += CV_THREADS) cp_async16(s_flow + comp * slots + woff + 4 * j, src + 4 * j);
+    }
+  };
   {
+    copy_pass(ti, 0, 0);
+    copy_flow(ti);
+    cp_async_commit();
     if (tid < 12)
       for (int d = 0; d <= CV_PF && d < nchunk; ++d) prefetch(ti, d);
     if (unit_ok(ti)) {
@@ -303,8 +326,10 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
       store_unit(reinterpret_cast<float4*>(smem_raw + g_off), u_p4, vg);
     }
   }
+  cp_async_wait_all();
   __syncthreads();
 
+  int pstage = 0;                                // s_pass stage being consumed
   unsigned char* cur = smem_raw;                 // stage being consumed
   unsigned char* oth = smem_raw + buf_bytes;     // stage being filled
   for (; tile < g.ntiles; tile += gridDim.x) {
@@ -325,8 +350,8 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
         const int sy = wr0 + r;
         if (sy >= wlo && sy < whi) {
           const int p = sy * W + col;
-          const Axis ax = axis_coord_fast(__ldg(xs + col), __ldg(fl + p), W, inv_w, w_pow2);
-          const Axis ay = axis_coord_fast(__ldg(ys + sy), __ldg(fl + p + 2 * (int64_t)HW), H, inv_h, h_pow2);
+          const Axis ax = axis_coord_fast(__ldg(xs + col), s_flow[i], W, inv_w, w_pow2);
+          const Axis ay = axis_coord_fast(__ldg(ys + sy), s_flow[slots + i], H, inv_h, h_pow2);
           s_ix[i] = ax.i; s_iy[i] = ay.i; s_an[i] = (ay.i0 << 16) | ax.i0;
           const int cr = r - g.HALO;
           if (cr >= 0 && cr < g.R) s_gate[cr * W + col] = (unsigned char)((ax.gmult != 0.f ? 1 : 0) | (ay.gmult != 0.f ? 2 : 0));
@@ -416,7 +441,6 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
         }
       }
     }
-    const float* gpass = gout + ((int64_t)ti.b * C * 4 + (ti.t ? 3 : 0)) * HW;   // + tpix, channel stride cs
     float* gxo = (ti.t ? gx2 : gx1) + ti.b * sB;
     const float* xg = (ti.t ? x2 : x1) + ti.b * sB;
     const bool ok_here = unit_ok(ti), ok_next = unit_ok(tn);
@@ -440,13 +464,17 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
         have_nxt = ok_next;
         if (have_nxt) { load_unit(nx, x_ptr(tn, 0), sC); load_unit(ng, g_ptr(tn, 0), cs); }
       }
+      if (ch + 1 < nchunk) copy_pass(ti, ch + 1, pstage ^ 1);
+      else if (has_next_tile) { copy_pass(tn, 0, pstage ^ 1); copy_flow(tn); }
+      cp_async_commit();
       const unsigned char* Xb = cur;
       const unsigned char* Gb = cur + g_off;
+      const float* Pb = s_pass + pstage * 4 * core;
 #pragma unroll
       for (int k = 0; k < CV_NP; ++k) {
         if (tpix[k] < 0) continue;
-        const float* gp = gpass + tpix[k];
-        const float p0 = __ldg(gp), p1 = __ldg(gp + cs), p2 = __ldg(gp + 2 * cs), p3 = __ldg(gp + 3 * cs);
+        const float* gp = Pb + tid + k * CV_THREADS;
+        const float p0 = gp[0], p1 = gp[core], p2 = gp[2 * core], p3 = gp[3 * core];
         // target side: gather the scatter (zero-weight padding instead of predicates)
         float2 a01 = f2(0.f, 0.f), a23 = f2(0.f, 0.f);
 #pragma unroll
@@ -510,12 +538,14 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
         o[0] = __fadd_rn(p0, a01.x); o[sC] = __fadd_rn(p1, a01.y);
         o[2 * sC] = __fadd_rn(p2, a23.x); o[3 * sC] = __fadd_rn(p3, a23.y);
       }
-      gpass += 4 * cs; gxo += 4 * sC; xg += 4 * sC;
+      gxo += 4 * sC; xg += 4 * sC;
       if (have_nxt) {
         store_unit(reinterpret_cast<float4*>(oth), u_p4, nx);
         store_unit(reinterpret_cast<float4*>(oth + g_off), u_p4, ng);
       }
       unsigned char* tmp = cur; cur = oth; oth = tmp;
+      pstage ^= 1;
+      cp_async_wait_all();
       __syncthreads();
     }
     // ---------------- phase 3: flow gradient of this tile ----------------
@@ -617,7 +647,8 @@ int warp_bwd_cvec(const float* gout, const float* x1, const float* x2, int64_t s
                   int W, cudaStream_t st) {
   CvGeom g;
   if (!cv_geometry(g, B, H, W, option(OPT_BWD_HALO))) return SMOW_ERANGE;
-  const size_t smem = 4 * (size_t)g.WR * W * sizeof(float4) + 3 * (size_t)g.WR * W * sizeof(float) +
+  const size_t smem = 4 * (size_t)g.WR * W * sizeof(float4) + 5 * (size_t)g.WR * W * sizeof(float) +
+                      8 * (size_t)g.R * W * sizeof(float) +
                       2 * (size_t)CV_KO * CV_NP * CV_THREADS * sizeof(float) + 4 * sizeof(int) + (size_t)g.R * W;
   static thread_local size_t configured = 0;
   if (int e = cv_prepare(warp_bwd_cvec_kernel, smem, configured)) return e;
