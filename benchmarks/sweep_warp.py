@@ -30,6 +30,9 @@ def peak():
     return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
 
 
+INNER = 4   # calls enqueued between one event pair, so host launch latency does not pad sub-100 us kernels
+
+
 def time_fn(fn, warm, iters):
     for _ in range(warm):
         fn()
@@ -38,10 +41,11 @@ def time_fn(fn, warm, iters):
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(INNER):
+            fn()
         e1.record()
         e1.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / INNER)
     return statistics.median(ts)
 
 

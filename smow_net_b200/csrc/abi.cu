@@ -18,6 +18,7 @@ static Knob g_knobs[OPT_COUNT] = {
     {"bwd_halo", {2}},
     {"fwd_rows", {8}},
     {"fwd_halo", {2}},
+    {"cvec_prefetch", {3}},      // L2 bulk-prefetch distance of the channel-vectorised kernels, in chunks (0 = off)
 };
 
 int fail(int code, const char* fmt, ...) {

@@ -33,6 +33,16 @@ template <typename T> __device__ __forceinline__ void stv(T* p, const Vec<T>& r)
   *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(r.v);
 }
 
+// (row, element) of flat vector index i; 32-bit division when the problem allows it (always, in practice)
+__device__ __forceinline__ void split_index(int64_t i, int64_t per_row, bool small, int64_t& row, int64_t& col) {
+  if (small) {
+    const uint32_t r = (uint32_t)i / (uint32_t)per_row;
+    row = r; col = (uint32_t)i - r * (uint32_t)per_row;
+  } else {
+    row = i / per_row; col = i - row * per_row;
+  }
+}
+
 struct LerpW { float a1, b1, a2, b2; };
 __device__ __forceinline__ LerpW lerp_weights() {
   LerpW w;
@@ -53,9 +63,12 @@ tlerp_cat_fwd_kernel(const T* __restrict__ dec, const T* __restrict__ s1, const 
   if ((int)blockIdx.x < lerp_blocks) {
     const LerpW lw = lerp_weights();
     const int64_t hwv = hw / V;
+    const bool small = n_lerp < (1ll << 31);
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_lerp; i += (int64_t)lerp_blocks * 256) {
-      const int64_t bc = i / hwv, e = (i - bc * hwv) * V;
-      const int64_t b = bc / Cs, c = bc - b * Cs;
+      int64_t bc, e, b, c;
+      split_index(i, hwv, small, bc, e);
+      e *= V;
+      split_index(bc, Cs, small, b, c);
       const T* p1 = s1 + b * sB + c * sC + e;
       const T* p2 = s2 + b * sB + c * sC + e;
       T* o = cat + ((b * Ct + Cd + c) * 4) * hw + e;
@@ -80,9 +93,12 @@ tlerp_cat_fwd_kernel(const T* __restrict__ dec, const T* __restrict__ s1, const 
   } else {
     const int cb = (int)gridDim.x - lerp_blocks;
     const int64_t per_b = (int64_t)Cd * 4 * hw / V;   // vectors of dec per pair
+    const bool small = n_copy < (1ll << 31);
     for (int64_t i = (int64_t)(blockIdx.x - lerp_blocks) * 256 + threadIdx.x; i < n_copy;
          i += (int64_t)cb * 256) {
-      const int64_t b = i / per_b, r = (i - b * per_b) * V;
+      int64_t b, r;
+      split_index(i, per_b, small, b, r);
+      r *= V;
       const T* src = dec + b * (int64_t)Cd * 4 * hw + r;
       T* dst = cat + b * (int64_t)Ct * 4 * hw + r;
       if constexpr (VECTOR) stv(dst, ldv_stream(src));
@@ -99,9 +115,12 @@ tlerp_cat_bwd_kernel(const T* __restrict__ gcat, T* __restrict__ g1, T* __restri
   const int Ct = Cd + Cs;
   const LerpW lw = lerp_weights();
   const int64_t hwv = hw / V;
+  const bool small = n < (1ll << 31);
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    const int64_t bc = i / hwv, e = (i - bc * hwv) * V;
-    const int64_t b = bc / Cs, c = bc - b * Cs;
+    int64_t bc, e, b, c;
+    split_index(i, hwv, small, bc, e);
+    e *= V;
+    split_index(bc, Cs, small, b, c);
     const T* g = gcat + ((b * Ct + Cd + c) * 4) * hw + e;
     T* o1 = g1 + b * sB + c * sC + e;
     T* o2 = g2 + b * sB + c * sC + e;

@@ -27,7 +27,7 @@ constexpr int CV_NP = 2;   // pixels per thread
 constexpr int CV_K = 6;    // register gather-list length (bilinear scatter: 4 sources per target on average)
 constexpr int CV_PF = 3;   // L2 prefetch distance, in channel chunks
 
-struct CvGeom { int R, HALO, DCAP, WR, U, nbands, ntiles; };
+struct CvGeom { int R, HALO, DCAP, WR, U, nbands, ntiles, PF; };
 
 // 16-byte slot swizzle: keeps both the transposed fill (lanes 4 pixels apart) and the tap reads
 // (lanes 1 pixel apart) free of bank conflicts.  Only the low 3 bits change.
@@ -104,7 +104,7 @@ warp_fwd_cvec_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
   };
   {  // prologue: first chunk -> buffer 0
     if (tid < 8)
-      for (int d = 1; d <= CV_PF && d < nchunk; ++d) prefetch(ti, d);
+      for (int d = 1; d <= g.PF && d < nchunk; ++d) prefetch(ti, d);
     if (unit_ok(ti)) { Unit v; load_unit(v, unit_ptr(ti, 0), sC); store_unit(buf0, u_p4, v); }
   }
   __syncthreads();
@@ -152,7 +152,7 @@ warp_fwd_cvec_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
     for (int ch = 0; ch < nchunk; ++ch) {
       // L2 prefetch CV_PF chunks ahead (this tile, else the next one)
       if (tid < 8) {
-        const int pc = ch + 1 + CV_PF;
+        const int pc = ch + 1 + g.PF;
         if (pc < nchunk) prefetch(ti, pc);
         else if (has_next_tile && pc - nchunk < nchunk) prefetch(tn, pc - nchunk);
       }
@@ -317,7 +317,7 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
     copy_flow(ti);
     cp_async_commit();
     if (tid < 12)
-      for (int d = 0; d <= CV_PF && d < nchunk; ++d) prefetch(ti, d);
+      for (int d = 0; d <= g.PF && d < nchunk; ++d) prefetch(ti, d);
     if (unit_ok(ti)) {
       Unit vx, vg;
       load_unit(vx, x_ptr(ti, 0), sC);
@@ -450,7 +450,7 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
     // ---------------- phase 2: chunks of 4 channels ----------------
     for (int ch = 0; ch < nchunk; ++ch) {
       if (tid < 14) {
-        const int pc = ch + 1 + CV_PF;
+        const int pc = ch + 1 + g.PF;
         if (pc < nchunk) prefetch(ti, pc);
         else if (has_next_tile && pc - nchunk < nchunk) prefetch(tn, pc - nchunk);
       }
@@ -614,6 +614,7 @@ static bool cv_geometry(CvGeom& g, int B, int H, int W, int halo) {
   if (g.U > CV_THREADS) return false;
   g.nbands = (H + R - 1) / R;
   g.ntiles = 2 * B * g.nbands;
+  g.PF = option(OPT_CVEC_PF);
   return true;
 }
 
