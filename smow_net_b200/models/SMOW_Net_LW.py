@@ -26,7 +26,10 @@ _DECODER = {1: (320, 640, 160), 2: (160, 256, 64), 3: (64, 96, 32), 4: (32, 56, 
 class SMOW_Net_LW(nn.Module):
     def __init__(self, pretrained=True):
         super().__init__()
-        self.backbone = mobilenet_v2(pretrained=pretrained)
+        # The 2-D Siamese backbone runs channels-last on the GPU: cuDNN's NHWC depthwise / pointwise kernels
+        # are ~2x faster on B200 than ATen's NCHW depthwise ones (benchmarks/e2e_probe.py: 44.3 -> 39.0 ms per
+        # batch-16 step).  Parameter shapes, names and values are unchanged.
+        self.backbone = mobilenet_v2(pretrained=pretrained).to(memory_format=torch.channels_last)
         self.OFW = OFW(16)
         self.MaxPool = spatial_max_pool()
         for k, (cdec, ccat, cout) in _DECODER.items():
@@ -38,10 +41,13 @@ class SMOW_Net_LW(nn.Module):
         self.sigmoid = nn.Sigmoid()
 
     def forward(self, x1, x2):
+        if x1.is_cuda:
+            x1 = x1.contiguous(memory_format=torch.channels_last)
+            x2 = x2.contiguous(memory_format=torch.channels_last)
         pyr1 = self.backbone(x1)                                # 5 levels, T1
         pyr2 = self.backbone(x2)                                # same weights, T2
 
-        x0 = torch.stack((pyr1[0], pyr2[0]), dim=2)             # (B,16,2,H/2,W/2), reference :38-40
+        x0 = torch.stack((pyr1[0], pyr2[0]), dim=2).contiguous()   # (B,16,2,H/2,W/2), reference :38-40
         tokens = self.Transformer_Encoder(self.OFW(x0))
 
         dec = self.MaxPool(ops.tlerp_pair_cat(None, pyr1[4], pyr2[4]))   # reference :71-73

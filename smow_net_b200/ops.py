@@ -38,12 +38,8 @@ def _dtype_code(t):
 
 def _layout5(t):
     """(tensor, layout code) with the tensor made dense in one of the two supported orders."""
-    if t.is_contiguous():
-        return t, _lib.NCDHW
-    if t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d):
-        return t, _lib.NDHWC
-    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
-        return t, _lib.NDHWC
+    # The C ABI defines SMOW_NDHWC, but this revision builds the NCDHW kernels only: a channels_last(_3d)
+    # tensor is brought to the contiguous order (one copy) rather than refused.
     return t.contiguous(), _lib.NCDHW
 
 
@@ -230,11 +226,16 @@ def flow_warp(input, flow, size=None):
     if size is not None and tuple(size) != tuple(input.shape[3:]):
         raise RuntimeError("flow_warp: size %s must equal the input's spatial size %s"
                            % (tuple(size), tuple(input.shape[3:])))
+    if input.shape[0] == 0:      # empty batch: nothing to launch (the reference returns an empty stack too)
+        _require_cuda(input, flow)
+        return input.new_zeros((0, input.shape[1], 4) + tuple(input.shape[3:])) + 0 * (input.sum() + flow.sum())
     return _WarpStack.apply(input, flow)
 
 
 def warp_pair(x_t1, x_t2, flow):
     """flow_warp on two un-stacked (B,C,H,W) frames -> (B,C,4,H,W)."""
+    if x_t1.shape[0] == 0:
+        return flow_warp(torch.stack((x_t1, x_t2), 2), flow)
     return _WarpPair.apply(x_t1, x_t2, flow)
 
 
@@ -317,14 +318,20 @@ class _TLerpPairCat(torch.autograd.Function):
 
 def tlerp_cat(dec, skip):
     """cat([dec, interpolate(skip, (4,h,w), trilinear, align_corners=True)], dim=1) in one launch."""
+    if skip.shape[0] == 0:
+        _require_cuda(dec, skip)
+        cd = 0 if dec is None else dec.shape[1]
+        return skip.new_zeros((0, cd + skip.shape[1], 4) + tuple(skip.shape[3:]))
     return _TLerpCat.apply(dec, skip)
 
 
 def tlerp(skip):
     """Temporal 2 -> 4 upsample alone: (B,C,2,h,w) -> (B,C,4,h,w)."""
-    return _TLerpCat.apply(None, skip)
+    return tlerp_cat(None, skip)
 
 
 def tlerp_pair_cat(dec, x_t1, x_t2):
     """tlerp_cat on two un-stacked (B,C,h,w) frames (dec may be None)."""
+    if x_t1.shape[0] == 0:
+        return tlerp_cat(dec, torch.stack((x_t1, x_t2), 2))
     return _TLerpPairCat.apply(dec, x_t1, x_t2)

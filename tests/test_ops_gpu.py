@@ -241,6 +241,34 @@ def test_tlerp_against_same_device_reference(case, dtype):
     assert torch.equal(a.grad, s1.grad[:, :, 0]) and torch.equal(b.grad, s1.grad[:, :, 1])
 
 
+def test_empty_batch_launches_nothing():
+    """Ragged / empty inputs: a zero-pair batch returns empty tensors of the right shape, like the reference."""
+    x = torch.zeros(0, 8, 2, 16, 16, device=DEV, requires_grad=True)
+    flow = torch.zeros(0, 2, 2, 16, 16, device=DEV)
+    before = _lib.launch_count()
+    out = ops.flow_warp(x, flow, (16, 16))
+    assert out.shape == (0, 8, 4, 16, 16) and _lib.launch_count() == before
+    out.sum().backward()
+    assert x.grad.shape == x.shape
+    assert ops.tlerp(x.detach()).shape == (0, 8, 4, 16, 16)
+    assert ops.tlerp_cat(torch.zeros(0, 3, 4, 16, 16, device=DEV), x.detach()).shape == (0, 11, 4, 16, 16)
+    assert ops.warp_pair(x.detach()[:, :, 0], x.detach()[:, :, 1], flow).shape == (0, 8, 4, 16, 16)
+
+
+def test_large_batch_config3_shape():
+    """Config 3's single-GPU shape (B=128, C=32, 128x128: 0.5 GiB in, 1 GiB out): pass-through slots exact,
+    warped slots equal to the same-device reference on a sample of pairs."""
+    g = torch.Generator(device=DEV).manual_seed(12)
+    x = torch.randn(128, 32, 2, 128, 128, device=DEV, generator=g)
+    flow = torch.randn(128, 2, 2, 128, 128, device=DEV, generator=g) * 0.4
+    with torch.no_grad():
+        out = ops.flow_warp(x, flow, (128, 128))
+        assert torch.equal(out[:, :, 0], x[:, :, 0]) and torch.equal(out[:, :, 3], x[:, :, 1])
+        for b in (0, 63, 127):
+            ref = torch_ref.ref_flow_warp(x[b:b + 1], flow[b:b + 1])
+            assert float((out[b:b + 1] - ref).abs().max()) <= 1e-6
+
+
 def test_launch_counter_counts_our_kernels():
     x = torch.randn(1, 4, 2, 16, 16, device=DEV)
     before = _lib.launch_count()
