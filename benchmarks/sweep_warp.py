@@ -1,14 +1,13 @@
 #!/usr/bin/env python
 """Isolated hot-path kernel sweep (BASELINE.json configs[4]): warp+stack fwd/bwd and tlerp+concat
 fwd/bwd, HBM-cold (working set >= --min-bytes, several times the 126 MB L2), CUDA-event timed, against the
-reference's own op sequence on the same GPU (oracle.torch_ref: F.grid_sample/F.interpolate/torch.cat =
-ATen's sm_100 kernels).
+reference's own op sequence on the same GPU (benchmarks/_aten_baseline.py: F.grid_sample / F.interpolate /
+torch.cat = ATen's sm_100 kernels).
 
     python benchmarks/sweep_warp.py [--quick] [--out gpurun_out/sweep.jsonl]
 
 One JSON line per (op, shape, dtype, variant): ms (median), algorithmic GB/s, fraction of the measured
-HBM peak, and the speed-up over the ATen sequence.  This script is measurement infrastructure: it may
-import oracle/ (as the baseline being compared against), the product never does.
+HBM peak, and the speed-up over the ATen sequence.
 """
 import argparse
 import json
@@ -18,10 +17,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import torch  # noqa: E402
 
-from oracle import torch_ref  # noqa: E402
+from _aten_baseline import aten_flow_warp, aten_tlerp_cat  # noqa: E402
 from smow_net_b200 import _lib, ops  # noqa: E402
 
 
@@ -77,11 +77,11 @@ def sweep_warp(args, emit):
                 if dtype == torch.float32:
                     xr, fr = x.clone().requires_grad_(True), flow.clone().requires_grad_(True)
                     with torch.no_grad():
-                        ref_f = time_fn(lambda: torch_ref.ref_flow_warp(x, flow), args.warm, args.iters)
+                        ref_f = time_fn(lambda: aten_flow_warp(x, flow), args.warm, args.iters)
 
                     def ref_fb():
                         xr.grad = fr.grad = None
-                        torch_ref.ref_flow_warp(xr, fr).backward(gout)
+                        aten_flow_warp(xr, fr).backward(gout)
                     ref_b = time_fn(ref_fb, args.warm, args.iters) - ref_f
                 for fv in args.fwd_variants:
                     _lib.set_option("warp_fwd_variant", fv)
@@ -123,7 +123,7 @@ def sweep_tlerp(args, emit):
             gcat = torch.randn(B, Cd + Cs, 4, h, h, device=dev, generator=g).to(dtype)
             base = {"Cd": Cd, "Cs": Cs, "h": h, "B": B, "dtype": str(dtype).split(".")[-1]}
             with torch.no_grad():
-                ref_f = time_fn(lambda: torch_ref.ref_tlerp_cat(dec, skip), args.warm, args.iters)
+                ref_f = time_fn(lambda: aten_tlerp_cat(dec, skip), args.warm, args.iters)
                 ms = time_fn(lambda: ops.tlerp_cat(dec, skip), args.warm, args.iters)
             nb = ops.tlerp_fwd_bytes(B, Cd, Cs, h * h, s)
             emit(dict(base, op="tlerp_cat_fwd", variant=0, ms=ms, gbps=nb / ms / 1e6, frac=nb / ms / 1e6 / peak(),
@@ -136,7 +136,7 @@ def sweep_tlerp(args, emit):
                 cat.backward(gcat, retain_graph=True)
             ms = time_fn(bwd, args.warm, args.iters)
             sr = skip.clone().requires_grad_(True)
-            catr = torch_ref.ref_tlerp_cat(dec, sr)
+            catr = aten_tlerp_cat(dec, sr)
 
             def rbwd():
                 sr.grad = None

@@ -76,3 +76,18 @@ def test_module_matches_oracle_routed_module_on_same_device(kind, monkeypatch):
         ref = model(x1, x2)
     assert float((mine - ref).abs().max()) <= 1e-5
     assert float(((mine > 0.5) != (ref > 0.5)).float().mean()) <= 1e-3
+
+
+def test_tiled_inference_matches_per_crop_calls():
+    """Config 4: a 512x768 scene tile is cut into 256x256 crops (the only size the reference network accepts),
+    run as one batch and re-assembled; every crop equals a direct call on that crop."""
+    from smow_net_b200.runtime import synthetic
+    model = helpers.seeded_model("lw", device=DEV).eval()
+    g = torch.Generator().manual_seed(17)
+    ta, tb = torch.randn(1, 3, 512, 768, generator=g).to(DEV), torch.randn(1, 3, 512, 768, generator=g).to(DEV)
+    with torch.no_grad():
+        prob = model(synthetic.tiles_to_crops(ta), synthetic.tiles_to_crops(tb))
+        full = synthetic.crops_to_tiles(prob, 1, 512, 768)
+        direct = model(ta[:, :, 256:512, 512:768].contiguous(), tb[:, :, 256:512, 512:768].contiguous())
+    assert full.shape == (1, 1, 512, 768)
+    assert float((full[:, :, 256:512, 512:768] - direct).abs().max()) <= 1e-5
