@@ -210,55 +210,7 @@ warp_fwd_cvec_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
 // ------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------
-constexpr int CV_KT = 8;   // gather-list entries per target staged in shared memory (the first CV_K move to registers)
-
-// One candidate source (window-local row offset rowo, column sx) of target (ty,tx): bilinear weight if its
-// footprint covers the target.  an = packed anchors (y0<<16|x0), ixs/iys = clipped sample coordinates.
-template <typename F>
-__device__ __forceinline__ void test_source(const int* __restrict__ an, const float* __restrict__ ixs,
-                                            const float* __restrict__ iys, int rowo, int sx, int ty, int tx, int dcap,
-                                            int& n, F&& f) {
-  const int a = an[rowo + sx];
-  const int x0 = a & 0xffff, y0 = a >> 16;
-  const unsigned ex = (unsigned)(tx - x0), ey = (unsigned)(ty - y0);
-  if ((ex | ey) > 1u) return;                                           // footprint does not cover the target
-  if ((unsigned)(x0 - sx + dcap) > (unsigned)(2 * dcap)) return;        // column displacement beyond DCAP: far kernel
-  const float ix = ixs[rowo + sx], iy = iys[rowo + sx];
-  const float x0f = (float)x0, y0f = (float)y0;
-  const float wx = ex ? __fsub_rn(ix, x0f) : __fsub_rn(__fadd_rn(x0f, 1.f), ix);
-  const float wy = ey ? __fsub_rn(iy, y0f) : __fsub_rn(__fadd_rn(y0f, 1.f), iy);
-  f(__fmul_rn(wx, wy), swz(rowo + sx) * 16, n);
-  ++n;
-}
-// all candidates in fixed (row-major) order; returns the number of sources found
-template <typename F>
-__device__ __forceinline__ int scan_sources(const int* __restrict__ an, const float* __restrict__ ixs,
-                                            const float* __restrict__ iys, int W, int wr0, int sy_a, int sy_b, int sx_a,
-                                            int sx_b, int ty, int tx, int dcap, F&& f) {
-  int n = 0;
-  for (int sy = sy_a; sy <= sy_b; ++sy)
-    for (int sx = sx_a; sx <= sx_b; ++sx) test_source(an, ixs, iys, (sy - wr0) * W, sx, ty, tx, dcap, n, f);
-  return n;
-}
-// same order, for the common sub-pixel case where the candidates fit a 3x3 block starting at (sy0, sx0): unrolled
-template <typename F>
-__device__ __forceinline__ int scan_sources_3x3(const int* __restrict__ an, const float* __restrict__ ixs,
-                                                const float* __restrict__ iys, int W, int wr0, int sy_a, int sy_b,
-                                                int sx_a, int sx_b, int sy0, int sx0, int ty, int tx, int dcap, F&& f) {
-  int n = 0;
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int sy = sy0 + dy;
-    if (sy < sy_a || sy > sy_b) continue;
-    const int rowo = (sy - wr0) * W;
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int sx = sx0 + dx;
-      if (sx >= sx_a && sx <= sx_b) test_source(an, ixs, iys, rowo, sx, ty, tx, dcap, n, f);
-    }
-  }
-  return n;
-}
+constexpr int CV_KO = 2;   // extra gather-list entries per target kept in shared memory (beyond CV_K)
 
 __device__ __forceinline__ bool cv_near_row(int sy, int ty, const CvGeom& g) {
   const int h0 = (ty / g.R) * g.R;
@@ -296,9 +248,9 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
   float* s_ix = reinterpret_cast<float*>(smem_raw + 2 * buf_bytes);
   float* s_iy = s_ix + slots;
   int* s_an = reinterpret_cast<int*>(s_iy + slots);                    // (y0 << 16) | x0 of every window pixel
-  float* s_ovw = reinterpret_cast<float*>(s_an + slots);               // gather-list weights [CV_KT][CV_NP][CV_THREADS]
-  int* s_ovo = reinterpret_cast<int*>(s_ovw + CV_KT * CV_NP * CV_THREADS);   // ... and source byte offsets
-  int* s_rng = s_ovo + CV_KT * CV_NP * CV_THREADS;
+  float* s_ovw = reinterpret_cast<float*>(s_an + slots);               // [CV_KO][CV_NP][CV_THREADS]
+  int* s_ovo = reinterpret_cast<int*>(s_ovw + CV_KO * CV_NP * CV_THREADS);
+  int* s_rng = s_ovo + CV_KO * CV_NP * CV_THREADS;
   float* s_pass = reinterpret_cast<float*>(s_rng + 4);                  // [2 stages][4 channels][R*W], cp.async filled
   float* s_flow = s_pass + 2 * 4 * g.R * W;                             // [2 components][WR*W] of the tile being prepared
   unsigned char* s_gate = reinterpret_cast<unsigned char*>(s_flow + 2 * slots);  // core pixels: bit0 = x gate, bit1 = y gate
@@ -420,8 +372,29 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
     const int dxlo = max(s_rng[0], -g.DCAP), dxhi = min(s_rng[1], g.DCAP);
     const int dylo = s_rng[2], dyhi = s_rng[3];
 
-    // candidate sources of a target: rows [ty-1-dyhi, ty-dylo] x columns [tx-1-dxhi, tx-dxlo], clipped to the window
-    const bool compact = (dxhi - dxlo <= 1) && (dyhi - dylo <= 1);   // tile-uniform: at most 3x3 candidates
+    // visit every source of target (ty,tx) in fixed order: f(weight, byte offset of the source slot, hit index)
+    auto probe = [&](int ty, int tx, auto&& f) {
+      int n = 0;
+      const int sy_a = max(wlo, ty - 1 - dyhi), sy_b = min(whi - 1, ty - dylo);
+      const int sx_a = max(0, tx - 1 - dxhi), sx_b = min(W - 1, tx - dxlo);
+      for (int sy = sy_a; sy <= sy_b; ++sy) {
+        const int rowo = (sy - wr0) * W;
+        for (int sx = sx_a; sx <= sx_b; ++sx) {
+          const int an = s_an[rowo + sx];
+          const int x0 = an & 0xffff, y0 = an >> 16;
+          const int ex = tx - x0, ey = ty - y0;
+          if ((unsigned)ex > 1u || (unsigned)ey > 1u) continue;
+          if (!cv_near_col(x0 - sx, g)) continue;
+          const float ix = s_ix[rowo + sx], iy = s_iy[rowo + sx];
+          const float x0f = (float)x0, y0f = (float)y0;
+          const float wx = ex ? __fsub_rn(ix, x0f) : __fsub_rn(__fadd_rn(x0f, 1.f), ix);
+          const float wy = ey ? __fsub_rn(iy, y0f) : __fsub_rn(__fadd_rn(y0f, 1.f), iy);
+          f(__fmul_rn(wx, wy), swz(rowo + sx) * 16, n);
+          ++n;
+        }
+      }
+      return n;
+    };
 
     // ---------------- phase 1: gather lists (targets) and footprints (sources) ----------------
     float lw[CV_NP][CV_K];
@@ -442,23 +415,15 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
       wx0[k] = wx1[k] = wy0[k] = wy1[k] = 0.f;
       if (p_r[k] < g.R && h < H) {
         tpix[k] = h * W + p_c[k];
-        {
-          const int ty = h, tx = p_c[k];
-          const int sy_a = max(wlo, ty - 1 - dyhi), sy_b = min(whi - 1, ty - dylo);
-          const int sx_a = max(0, tx - 1 - dxhi), sx_b = min(W - 1, tx - dxlo);
-          float* lwk = s_ovw + k * CV_THREADS + tid;      // this thread's column of the [CV_KT][CV_NP][CV_THREADS] tables
-          int* lok = s_ovo + k * CV_THREADS + tid;
-          auto keep = [&](float w, int off, int n) {
-            if (n < CV_KT) { lwk[n * CV_NP * CV_THREADS] = w; lok[n * CV_NP * CV_THREADS] = off; }
-          };
-          int n;
-          if (compact) n = scan_sources_3x3(s_an, s_ix, s_iy, W, wr0, sy_a, sy_b, sx_a, sx_b, ty - 1 - dyhi, tx - 1 - dxhi, ty, tx, g.DCAP, keep);
-          else n = scan_sources(s_an, s_ix, s_iy, W, wr0, sy_a, sy_b, sx_a, sx_b, ty, tx, g.DCAP, keep);
-          ln[k] = n;
+        ln[k] = probe(h, p_c[k], [&](float w, int off, int n) {
 #pragma unroll
           for (int j = 0; j < CV_K; ++j)
-            if (j < n) { lw[k][j] = lwk[j * CV_NP * CV_THREADS]; lo[k][j] = lok[j * CV_NP * CV_THREADS]; }
-        }
+            if (n == j) { lw[k][j] = w; lo[k][j] = off; }
+          if (n >= CV_K && n < CV_K + CV_KO) {
+            s_ovw[((n - CV_K) * CV_NP + k) * CV_THREADS + tid] = w;
+            s_ovo[((n - CV_K) * CV_NP + k) * CV_THREADS + tid] = off;
+          }
+        });
         // own pixel as a source: footprint from the phase-0 tables
         const float ix = s_ix[ownp], iy = s_iy[ownp];
         const int an = s_an[ownp];
@@ -518,19 +483,17 @@ warp_bwd_cvec_kernel(const float* __restrict__ gout, const float* __restrict__ x
           a01 = __ffma2_rn(bc(lw[k][j]), f2(v.x, v.y), a01);
           a23 = __ffma2_rn(bc(lw[k][j]), f2(v.z, v.w), a23);
         }
-        if (ln[k] > CV_K) {                       // rare: entries CV_K .. CV_KT-1 stay in shared memory
-          const int ne = min(ln[k], CV_KT);
-          for (int j = CV_K; j < ne; ++j) {
+        if (ln[k] > CV_K) {                       // rare: entries CV_K .. CV_K+CV_KO-1 live in shared memory
+          const int ne = min(ln[k], CV_K + CV_KO) - CV_K;
+          for (int j = 0; j < ne; ++j) {
             const float w = s_ovw[(j * CV_NP + k) * CV_THREADS + tid];
             const float4 v = *reinterpret_cast<const float4*>(Gb + s_ovo[(j * CV_NP + k) * CV_THREADS + tid]);
             a01 = __ffma2_rn(bc(w), f2(v.x, v.y), a01);
             a23 = __ffma2_rn(bc(w), f2(v.z, v.w), a23);
           }
-          if (ln[k] > CV_KT) {                    // very rare: strongly converging flow, re-scan
-            const int ty = ti.h0 + p_r[k], tx = p_c[k];
-            scan_sources(s_an, s_ix, s_iy, W, wr0, max(wlo, ty - 1 - dyhi), min(whi - 1, ty - dylo), max(0, tx - 1 - dxhi),
-                         min(W - 1, tx - dxlo), ty, tx, g.DCAP, [&](float w, int off, int n) {
-              if (n >= CV_KT) {
+          if (ln[k] > CV_K + CV_KO) {             // very rare: strongly converging flow, re-probe
+            probe(ti.h0 + p_r[k], p_c[k], [&](float w, int off, int n) {
+              if (n >= CV_K + CV_KO) {
                 const float4 v = *reinterpret_cast<const float4*>(Gb + off);
                 a01 = __ffma2_rn(bc(w), f2(v.x, v.y), a01);
                 a23 = __ffma2_rn(bc(w), f2(v.z, v.w), a23);
@@ -687,7 +650,7 @@ int warp_bwd_cvec(const float* gout, const float* x1, const float* x2, int64_t s
   if (!cv_geometry(g, B, H, W, option(OPT_BWD_HALO))) return SMOW_ERANGE;
   const size_t smem = 4 * (size_t)g.WR * W * sizeof(float4) + 5 * (size_t)g.WR * W * sizeof(float) +
                       8 * (size_t)g.R * W * sizeof(float) +
-                      2 * (size_t)CV_KT * CV_NP * CV_THREADS * sizeof(float) + 4 * sizeof(int) + (size_t)g.R * W;
+                      2 * (size_t)CV_KO * CV_NP * CV_THREADS * sizeof(float) + 4 * sizeof(int) + (size_t)g.R * W;
   static thread_local size_t configured = 0;
   if (int e = cv_prepare(warp_bwd_cvec_kernel, smem, configured)) return e;
   const int sms = device_info().sms * CV_CTAS;
