@@ -63,7 +63,9 @@ def wrap_ddp(model, device, world):
     # per-replica BatchNorm statistics (no SyncBN, no buffer broadcast) — the reference's regime
     # 5.5 M (LW) / 22 M (S-net) fp32 gradients: 8 MB buckets give 3 / 11 all-reduces that overlap the backward
     # (the default 25 MB would leave SMOW_Net_LW with a single, un-overlapped all-reduce at the very end)
-    return DDP(model, device_ids=ids, broadcast_buffers=False, gradient_as_bucket_view=True, bucket_cap_mb=8)
+    cap = float(os.environ.get("SMOW_DDP_BUCKET_MB", "8"))
+    return DDP(model, device_ids=ids, broadcast_buffers=False, gradient_as_bucket_view=True, bucket_cap_mb=cap,
+               static_graph=os.environ.get("SMOW_DDP_STATIC", "0") == "1")
 
 
 def max_over_ranks(value, device, world):
