@@ -143,6 +143,78 @@ tlerp_cat_bwd_kernel(const T* __restrict__ gcat, T* __restrict__ g1, T* __restri
   }
 }
 
+
+// ------------------------------------------------------------------------------
+// channels-last (NDHWC) variants: memory order (B, T, h*w, C); vectors run along C
+// ------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, const T* __restrict__ s2,
+                           int64_t sB, T* __restrict__ cat, int Cd, int Cs, int64_t hw, int64_t n_lerp,
+                           int64_t n_copy, int lerp_blocks) {
+  constexpr int V = Vec<T>::N;
+  const int Ct = Cd + Cs;
+  if ((int)blockIdx.x < lerp_blocks) {
+    const LerpW lw = lerp_weights();
+    const int64_t qs = Cs / V;
+    const bool small = n_lerp < (1ll << 31);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_lerp; i += (int64_t)lerp_blocks * 256) {
+      int64_t bp, vs, b, p;
+      split_index(i, qs, small, bp, vs);
+      split_index(bp, hw, small, b, p);
+      const T* p1 = s1 + b * sB + p * Cs + vs * V;
+      const T* p2 = s2 + b * sB + p * Cs + vs * V;
+      T* o = cat + ((b * 4) * hw + p) * Ct + Cd + vs * V;
+      const Vec<T> a = ldv(p1), bb = ldv(p2);
+      Vec<T> m1, m2;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float fa = cvtf<T>(a.v[j]), fb = cvtf<T>(bb.v[j]);
+        m1.v[j] = fromf<T>(fmaf(lw.a1, fa, __fmul_rn(lw.b1, fb)));
+        m2.v[j] = fromf<T>(fmaf(lw.a2, fa, __fmul_rn(lw.b2, fb)));
+      }
+      const int64_t fs = hw * Ct;    // frame stride of cat
+      stv(o, a); stv(o + fs, m1); stv(o + 2 * fs, m2); stv(o + 3 * fs, bb);
+    }
+  } else {
+    const int cb = (int)gridDim.x - lerp_blocks;
+    const int64_t qd = Cd / V;
+    const bool small = n_copy < (1ll << 31);
+    for (int64_t i = (int64_t)(blockIdx.x - lerp_blocks) * 256 + threadIdx.x; i < n_copy; i += (int64_t)cb * 256) {
+      int64_t r, vd;
+      split_index(i, qd, small, r, vd);        // r = (b*4 + slot)*hw + p
+      stv(cat + r * Ct + vd * V, ldv_stream(dec + r * Cd + vd * V));
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+tlerp_cat_bwd_ndhwc_kernel(const T* __restrict__ gcat, T* __restrict__ g1, T* __restrict__ g2, int64_t sB, int Cd,
+                           int Cs, int64_t hw, int64_t n) {
+  constexpr int V = Vec<T>::N;
+  const int Ct = Cd + Cs;
+  const LerpW lw = lerp_weights();
+  const int64_t qs = Cs / V, fs = hw * Ct;
+  const bool small = n < (1ll << 31);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    int64_t bp, vs, b, p;
+    split_index(i, qs, small, bp, vs);
+    split_index(bp, hw, small, b, p);
+    const T* g = gcat + ((b * 4) * hw + p) * Ct + Cd + vs * V;
+    const Vec<T> a = ldv_stream(g), m1 = ldv_stream(g + fs), m2 = ldv_stream(g + 2 * fs), d = ldv_stream(g + 3 * fs);
+    Vec<T> r1, r2;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float f0 = cvtf<T>(a.v[j]), f1 = cvtf<T>(m1.v[j]), f2 = cvtf<T>(m2.v[j]), f3 = cvtf<T>(d.v[j]);
+      r1.v[j] = fromf<T>(fmaf(lw.a2, f2, fmaf(lw.a1, f1, f0)));
+      r2.v[j] = fromf<T>(__fadd_rn(fmaf(lw.b2, f2, __fmul_rn(lw.b1, f1)), f3));
+    }
+    stv(g1 + b * sB + p * Cs + vs * V, r1);
+    stv(g2 + b * sB + p * Cs + vs * V, r2);
+  }
+}
+
 // ------------------------------------------------------------------------------
 // host dispatch
 // ------------------------------------------------------------------------------
@@ -185,11 +257,43 @@ static int bwd_impl(const T* gcat, T* g1, T* g2, int64_t sB, int64_t sC, int B, 
   return check_launch("tlerp_cat_bwd");
 }
 
+template <typename T>
+static int fwd_ndhwc(const T* dec, const T* s1, const T* s2, int64_t sB, T* cat, int B, int Cd, int Cs, int64_t hw,
+                     cudaStream_t st) {
+  constexpr int V = Vec<T>::N;
+  const bool do_lerp = s1 != nullptr, do_copy = dec != nullptr && Cd > 0;
+  if (!do_lerp && !do_copy) return 0;
+  if (Cd % V || Cs % V || !aligned16(cat) || (do_lerp && (!aligned16(s1) || !aligned16(s2) || sB % V)) ||
+      (do_copy && !aligned16(dec)))
+    return fail(SMOW_EALIGN, "tlerp_cat NDHWC needs Cd, Cs multiples of %d and 16 B aligned tensors", V);
+  const int64_t n_lerp = do_lerp ? (int64_t)B * hw * (Cs / V) : 0;
+  const int64_t n_copy = do_copy ? (int64_t)B * 4 * hw * (Cd / V) : 0;
+  const int cap = device_info().sms * 8;
+  const int lb = (int)((n_lerp + 255) / 256 < cap ? (n_lerp + 255) / 256 : cap);
+  const int cb = (int)((n_copy + 511) / 512 < cap ? (n_copy + 511) / 512 : cap);
+  tlerp_cat_fwd_ndhwc_kernel<T><<<lb + cb, 256, 0, st>>>(dec, s1, s2, sB, cat, Cd, Cs, hw, n_lerp, n_copy, lb);
+  count_launch();
+  return check_launch("tlerp_cat_fwd (NDHWC)");
+}
+
+template <typename T>
+static int bwd_ndhwc(const T* gcat, T* g1, T* g2, int64_t sB, int B, int Cd, int Cs, int64_t hw, cudaStream_t st) {
+  constexpr int V = Vec<T>::N;
+  if (Cd % V || Cs % V || !aligned16(gcat) || !aligned16(g1) || !aligned16(g2) || sB % V)
+    return fail(SMOW_EALIGN, "tlerp_cat NDHWC needs Cd, Cs multiples of %d and 16 B aligned tensors", V);
+  const int64_t n = (int64_t)B * hw * (Cs / V);
+  const int cap = device_info().sms * 8;
+  const int nb = (int)((n + 255) / 256 < cap ? (n + 255) / 256 : cap);
+  tlerp_cat_bwd_ndhwc_kernel<T><<<nb, 256, 0, st>>>(gcat, g1, g2, sB, Cd, Cs, hw, n);
+  count_launch();
+  return check_launch("tlerp_cat_bwd (NDHWC)");
+}
+
 static int check_args(const void* cat, int B, int Cd, int Cs, int64_t hw, int dtype, int layout) {
   if (!cat) return fail(SMOW_EINVAL, "null pointer argument");
   if (B <= 0 || Cd < 0 || Cs <= 0 || hw <= 0) return fail(SMOW_EINVAL, "bad shape B=%d Cd=%d Cs=%d hw=%lld", B, Cd, Cs, (long long)hw);
   if (dtype != SMOW_F32 && dtype != SMOW_BF16) return fail(SMOW_EDTYPE, "unsupported dtype %d", dtype);
-  if (layout != SMOW_NCDHW) return fail(SMOW_EDTYPE, "tlerp_cat: only the NCDHW layout is built");
+  if (layout != SMOW_NCDHW && layout != SMOW_NDHWC) return fail(SMOW_EDTYPE, "unsupported layout %d", layout);
   return 0;
 }
 
@@ -204,6 +308,13 @@ int smow_tlerp_pair_cat_fwd(const void* dec, const void* skip_t1, const void* sk
   if (int e = check_args(cat, B, Cd, Cs, hw, dtype, layout)) return e;
   if ((skip_t1 == nullptr) != (skip_t2 == nullptr)) return fail(SMOW_EINVAL, "skip_t1/skip_t2 must both be set or both be NULL");
   cudaStream_t st = (cudaStream_t)stream;
+  if (layout == SMOW_NDHWC) {
+    if (dtype == SMOW_F32)
+      return fwd_ndhwc<float>((const float*)dec, (const float*)skip_t1, (const float*)skip_t2, Cs * hw, (float*)cat, B,
+                              Cd, Cs, hw, st);
+    return fwd_ndhwc<__nv_bfloat16>((const __nv_bfloat16*)dec, (const __nv_bfloat16*)skip_t1,
+                                    (const __nv_bfloat16*)skip_t2, Cs * hw, (__nv_bfloat16*)cat, B, Cd, Cs, hw, st);
+  }
   if (dtype == SMOW_F32)
     return fwd_impl<float>((const float*)dec, (const float*)skip_t1, (const float*)skip_t2, Cs * hw, hw,
                            (float*)cat, B, Cd, Cs, hw, st);
@@ -215,6 +326,15 @@ int smow_tlerp_cat_fwd(const void* dec, const void* skip, void* cat, int B, int 
                        int dtype, int layout, void* stream) {
   if (int e = check_args(cat, B, Cd, Cs, hw, dtype, layout)) return e;
   cudaStream_t st = (cudaStream_t)stream;
+  if (layout == SMOW_NDHWC) {   // stacked channels_last_3d: frame 2 starts hw*Cs elements after frame 1
+    if (dtype == SMOW_F32) {
+      const float* s = (const float*)skip;
+      return fwd_ndhwc<float>((const float*)dec, s, s ? s + hw * Cs : nullptr, 2 * Cs * hw, (float*)cat, B, Cd, Cs, hw, st);
+    }
+    const __nv_bfloat16* s = (const __nv_bfloat16*)skip;
+    return fwd_ndhwc<__nv_bfloat16>((const __nv_bfloat16*)dec, s, s ? s + hw * Cs : nullptr, 2 * Cs * hw,
+                                    (__nv_bfloat16*)cat, B, Cd, Cs, hw, st);
+  }
   if (dtype == SMOW_F32) {
     const float* s = (const float*)skip;
     return fwd_impl<float>((const float*)dec, s, s ? s + hw : nullptr, 2 * Cs * hw, 2 * hw, (float*)cat, B, Cd,
@@ -230,6 +350,12 @@ int smow_tlerp_pair_cat_bwd(const void* gcat, void* gskip_t1, void* gskip_t2, in
   if (int e = check_args(gcat, B, Cd, Cs, hw, dtype, layout)) return e;
   if (!gskip_t1 || !gskip_t2) return fail(SMOW_EINVAL, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
+  if (layout == SMOW_NDHWC) {
+    if (dtype == SMOW_F32)
+      return bwd_ndhwc<float>((const float*)gcat, (float*)gskip_t1, (float*)gskip_t2, Cs * hw, B, Cd, Cs, hw, st);
+    return bwd_ndhwc<__nv_bfloat16>((const __nv_bfloat16*)gcat, (__nv_bfloat16*)gskip_t1, (__nv_bfloat16*)gskip_t2,
+                                    Cs * hw, B, Cd, Cs, hw, st);
+  }
   if (dtype == SMOW_F32)
     return bwd_impl<float>((const float*)gcat, (float*)gskip_t1, (float*)gskip_t2, Cs * hw, hw, B, Cd, Cs, hw, st);
   return bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)gcat, (__nv_bfloat16*)gskip_t1, (__nv_bfloat16*)gskip_t2,
@@ -241,6 +367,14 @@ int smow_tlerp_cat_bwd(const void* gcat, void* gskip, int B, int Cd, int Cs, int
   if (int e = check_args(gcat, B, Cd, Cs, hw, dtype, layout)) return e;
   if (!gskip) return fail(SMOW_EINVAL, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
+  if (layout == SMOW_NDHWC) {
+    if (dtype == SMOW_F32) {
+      float* g = (float*)gskip;
+      return bwd_ndhwc<float>((const float*)gcat, g, g + hw * Cs, 2 * Cs * hw, B, Cd, Cs, hw, st);
+    }
+    __nv_bfloat16* g = (__nv_bfloat16*)gskip;
+    return bwd_ndhwc<__nv_bfloat16>((const __nv_bfloat16*)gcat, g, g + hw * Cs, 2 * Cs * hw, B, Cd, Cs, hw, st);
+  }
   if (dtype == SMOW_F32) {
     float* g = (float*)gskip;
     return bwd_impl<float>((const float*)gcat, g, g + hw, 2 * Cs * hw, 2 * hw, B, Cd, Cs, hw, st);

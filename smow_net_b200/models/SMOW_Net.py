@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .blocks import DoubleConv3d, PointwiseConvBN, TemporalDeconvMix, spatial_max_pool
+from .blocks import DoubleConv3d, PointwiseConvBN, TemporalDeconvMix, convs_channels_last_3d, spatial_max_pool
 from .encoder3d import ResNet3D
 from .ofw import OFW
 from .tokens import Classifier, Transformer_Decoder, Transformer_Encoder
@@ -41,6 +41,7 @@ class SMOW_Net(nn.Module):
         self.Transformer_Decoder = Transformer_Decoder(in_chan=128)
         self.decoder = Classifier(in_chan=128, n_class=1)
         self.sigmoid = nn.Sigmoid()
+        convs_channels_last_3d(self)
 
     def forward(self, x1, x2):
         x = torch.stack((x1, x2), dim=2)                       # (B,3,2,H,W), reference :40-42

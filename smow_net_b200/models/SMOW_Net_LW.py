@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .blocks import SpatialConvMix, TemporalDeconvMix, spatial_max_pool
+from .blocks import SpatialConvMix, TemporalDeconvMix, convs_channels_last_3d, spatial_max_pool
 from .mobilenet import mobilenet_v2
 from .ofw import OFW
 from .tokens import Classifier, Transformer_Decoder, Transformer_Encoder
@@ -39,6 +39,7 @@ class SMOW_Net_LW(nn.Module):
         self.Transformer_Decoder = Transformer_Decoder(in_chan=64)
         self.decoder = Classifier(in_chan=64, n_class=1)
         self.sigmoid = nn.Sigmoid()
+        convs_channels_last_3d(self)
 
     def forward(self, x1, x2):
         if x1.is_cuda:

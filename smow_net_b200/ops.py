@@ -36,10 +36,20 @@ def _dtype_code(t):
         raise RuntimeError("smow_net_b200: unsupported dtype %s (fp32 and bf16 only)" % t.dtype)
 
 
-def _layout5(t):
-    """(tensor, layout code) with the tensor made dense in one of the two supported orders."""
-    # The C ABI defines SMOW_NDHWC, but this revision builds the NCDHW kernels only: a channels_last(_3d)
-    # tensor is brought to the contiguous order (one copy) rather than refused.
+def _is_channels_last(t):
+    fmt = torch.channels_last_3d if t.dim() == 5 else torch.channels_last
+    return (not t.is_contiguous()) and t.is_contiguous(memory_format=fmt)
+
+
+def _vec(t):
+    return 16 // t.element_size()          # channels per 16-byte vector
+
+
+def _layout5(t, *channel_counts, ndhwc_ok=True):
+    """(dense tensor, layout code).  A channels_last / channels_last_3d tensor keeps its order (NDHWC kernels)
+    when every channel count is a multiple of the 16-byte vector; anything else becomes contiguous NCDHW."""
+    if ndhwc_ok and _is_channels_last(t) and all(c % _vec(t) == 0 for c in channel_counts):
+        return t, _lib.NDHWC
     return t.contiguous(), _lib.NCDHW
 
 
@@ -148,7 +158,7 @@ class _WarpStack(torch.autograd.Function):
         B, C, _, H, W = x.shape
         if tuple(flow.shape) != (B, 2, 2, H, W):
             raise RuntimeError("flow_warp: flow must be (B,2,2,H,W)=%s, got %s" % ((B, 2, 2, H, W), tuple(flow.shape)))
-        x, layout = _layout5(x)
+        x, layout = _layout5(x, C, ndhwc_ok=x.dtype == torch.float32)
         flow = flow.float().contiguous()
         out = _empty((B, C, 4, H, W), x, layout)
         xs, ys = base_grid(W, x.device), base_grid(H, x.device)
@@ -186,7 +196,7 @@ class _WarpPair(torch.autograd.Function):
         B, C, H, W = x1.shape
         if tuple(flow.shape) != (B, 2, 2, H, W):
             raise RuntimeError("warp_pair: flow must be (B,2,2,H,W)")
-        x1, layout = _layout5(x1)
+        x1, layout = _layout5(x1, C, ndhwc_ok=x1.dtype == torch.float32)
         x2 = _as_layout(x2, layout)
         flow = flow.float().contiguous()
         out = _empty((B, C, 4, H, W), x1, layout)
@@ -248,32 +258,36 @@ class _TLerpCat(torch.autograd.Function):
             raise RuntimeError("tlerp_cat: skip must be (B,Cs,2,h,w), got %s" % (tuple(skip.shape),))
         B, Cs, _, h, w = skip.shape
         Cd = 0
-        skip = skip.contiguous()
         if dec is not None:
             if dec.dim() != 5 or dec.shape[0] != B or dec.shape[2] != 4 or tuple(dec.shape[3:]) != (h, w):
                 raise RuntimeError("tlerp_cat: dec must be (B,Cd,4,h,w) matching skip, got %s" % (tuple(dec.shape),))
             if dec.dtype != skip.dtype:
                 raise RuntimeError("tlerp_cat: dec and skip dtypes differ")
-            dec = dec.contiguous()
             Cd = dec.shape[1]
-        cat = torch.empty((B, Cd + Cs, 4, h, w), dtype=skip.dtype, device=skip.device)
+        # the concat follows the decoder tensor's order (the larger operand), else the skip's
+        skip, layout = _layout5(skip if dec is None or not _is_channels_last(dec) else
+                                skip.contiguous(memory_format=torch.channels_last_3d), Cd, Cs)
+        if dec is not None:
+            dec = _as_layout(dec, layout)
+        cat = _empty((B, Cd + Cs, 4, h, w), skip, layout)
         lib = _lib.load()
         with torch.cuda.device_of(skip):
             _call("tlerp_cat_fwd", tlerp_fwd_bytes(B, Cd, Cs, h * w, skip.element_size()), lib.smow_tlerp_cat_fwd,
                   dec.data_ptr() if dec is not None else None, skip.data_ptr(), cat.data_ptr(),
-                  B, Cd, Cs, h * w, _dtype_code(skip), _lib.NCDHW, _stream())
+                  B, Cd, Cs, h * w, _dtype_code(skip), layout, _stream())
         ctx.dims = (B, Cd, Cs, h, w)
+        ctx.layout = layout
         return cat
 
     @staticmethod
     def backward(ctx, gcat):
         B, Cd, Cs, h, w = ctx.dims
-        gcat = gcat.contiguous()
-        gskip = torch.empty((B, Cs, 2, h, w), dtype=gcat.dtype, device=gcat.device)
+        gcat = _as_layout(gcat, ctx.layout)
+        gskip = _empty((B, Cs, 2, h, w), gcat, ctx.layout)
         lib = _lib.load()
         with torch.cuda.device_of(gcat):
             _call("tlerp_cat_bwd", tlerp_bwd_bytes(B, Cs, h * w, gcat.element_size()), lib.smow_tlerp_cat_bwd,
-                  gcat.data_ptr(), gskip.data_ptr(), B, Cd, Cs, h * w, _dtype_code(gcat), _lib.NCDHW, _stream())
+                  gcat.data_ptr(), gskip.data_ptr(), B, Cd, Cs, h * w, _dtype_code(gcat), ctx.layout, _stream())
         gdec = gcat[:, :Cd] if Cd > 0 else None  # strided view, as torch.cat's backward returns
         return gdec, gskip
 
@@ -285,33 +299,37 @@ class _TLerpPairCat(torch.autograd.Function):
         if a.dim() != 4 or a.shape != b.shape or a.dtype != b.dtype:
             raise RuntimeError("tlerp_pair_cat: frames must be matching (B,Cs,h,w) tensors")
         B, Cs, h, w = a.shape
-        a, b = a.contiguous(), b.contiguous()
         Cd = 0
         if dec is not None:
             if dec.dim() != 5 or dec.shape[0] != B or dec.shape[2] != 4 or tuple(dec.shape[3:]) != (h, w):
                 raise RuntimeError("tlerp_pair_cat: dec must be (B,Cd,4,h,w) matching the frames")
-            dec = dec.contiguous()
             Cd = dec.shape[1]
-        cat = torch.empty((B, Cd + Cs, 4, h, w), dtype=a.dtype, device=a.device)
+        a, layout = _layout5(a if dec is None or not _is_channels_last(dec) else
+                             a.contiguous(memory_format=torch.channels_last), Cd, Cs)
+        b = _as_layout(b, layout)
+        if dec is not None:
+            dec = _as_layout(dec, layout)
+        cat = _empty((B, Cd + Cs, 4, h, w), a, layout)
         lib = _lib.load()
         with torch.cuda.device_of(a):
             _call("tlerp_cat_fwd", tlerp_fwd_bytes(B, Cd, Cs, h * w, a.element_size()), lib.smow_tlerp_pair_cat_fwd,
                   dec.data_ptr() if dec is not None else None, a.data_ptr(), b.data_ptr(), cat.data_ptr(),
-                  B, Cd, Cs, h * w, _dtype_code(a), _lib.NCDHW, _stream())
+                  B, Cd, Cs, h * w, _dtype_code(a), layout, _stream())
         ctx.dims = (B, Cd, Cs, h, w)
+        ctx.layout = layout
         return cat
 
     @staticmethod
     def backward(ctx, gcat):
         B, Cd, Cs, h, w = ctx.dims
-        gcat = gcat.contiguous()
-        ga = torch.empty((B, Cs, h, w), dtype=gcat.dtype, device=gcat.device)
-        gb = torch.empty_like(ga)
+        gcat = _as_layout(gcat, ctx.layout)
+        ga = _empty((B, Cs, h, w), gcat, ctx.layout)
+        gb = _empty((B, Cs, h, w), gcat, ctx.layout)
         lib = _lib.load()
         with torch.cuda.device_of(gcat):
             _call("tlerp_cat_bwd", tlerp_bwd_bytes(B, Cs, h * w, gcat.element_size()), lib.smow_tlerp_pair_cat_bwd,
                   gcat.data_ptr(), ga.data_ptr(), gb.data_ptr(), B, Cd, Cs, h * w, _dtype_code(gcat),
-                  _lib.NCDHW, _stream())
+                  ctx.layout, _stream())
         gdec = gcat[:, :Cd] if Cd > 0 else None
         return gdec, ga, gb
 

@@ -274,3 +274,66 @@ def test_launch_counter_counts_our_kernels():
     before = _lib.launch_count()
     ops.tlerp(x)
     assert _lib.launch_count() == before + 1
+
+
+# ---------------------------------------------------------------------------------- channels-last (NDHWC) kernels
+CL3 = torch.channels_last_3d
+
+
+@pytest.mark.parametrize("case", [(4, 16, 128, 128, 0.3), (2, 32, 128, 128, 1.0), (2, 64, 64, 64, 8.0), (1, 8, 37, 52, 2.0),
+                                  (1, 256, 32, 32, 0.5), (2, 12, 40, 24, 3.0)])
+def test_warp_ndhwc_against_same_device_reference(case):
+    """channels_last_3d in -> channels_last_3d out (vector-gather forward, vector-atomic backward)."""
+    B, C, H, W, sigma = case
+    g = torch.Generator(device=DEV).manual_seed(C + H)
+    x = torch.randn(B, C, 2, H, W, device=DEV, generator=g).contiguous(memory_format=CL3)
+    flow = torch.randn(B, 2, 2, H, W, device=DEV, generator=g) * sigma
+    gout = torch.randn(B, C, 4, H, W, device=DEV, generator=g).contiguous(memory_format=CL3)
+    xr, fr = x.clone(memory_format=torch.preserve_format).requires_grad_(True), flow.clone().requires_grad_(True)
+    before = _lib.launch_count()
+    out = ops.flow_warp(xr, fr, (H, W))
+    assert out.is_contiguous(memory_format=CL3) and _lib.launch_count() == before + 1
+    out.backward(gout)
+    assert xr.grad.is_contiguous(memory_format=CL3)
+    check_warp((out.detach(), xr.grad, fr.grad), torch_ref.warp_with_grads(x, flow, gout))
+    assert torch.equal(out[:, :, 0], x[:, :, 0]) and torch.equal(out[:, :, 3], x[:, :, 1])
+
+
+def test_warp_ndhwc_bf16_forward():
+    g = torch.Generator(device=DEV).manual_seed(2)
+    x = torch.randn(2, 32, 2, 64, 64, device=DEV, generator=g).bfloat16().contiguous(memory_format=CL3)
+    flow = torch.randn(2, 2, 2, 64, 64, device=DEV, generator=g) * 0.5
+    with torch.no_grad():
+        out = ops.flow_warp(x, flow, (64, 64))     # bf16 takes the NCDHW kernels (NDHWC backward is fp32-only)
+        ref = torch_ref.ref_flow_warp(x.float(), flow)
+    assert float((out.float() - ref).abs().max()) <= 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", [(28, 16, 128), (32, 24, 64), (64, 32, 32), (160, 96, 16), (320, 320, 8), (0, 16, 16), (256, 256, 8)])
+def test_tlerp_ndhwc_against_same_device_reference(case, dtype):
+    Cd, Cs, h = case
+    B = 2
+    g = torch.Generator(device=DEV).manual_seed(Cd + Cs + h)
+    skip = torch.randn(B, Cs, 2, h, h, device=DEV, generator=g).to(dtype).contiguous(memory_format=CL3)
+    dec = torch.randn(B, Cd, 4, h, h, device=DEV, generator=g).to(dtype).contiguous(memory_format=CL3) if Cd else None
+    gcat = torch.randn(B, Cd + Cs, 4, h, h, device=DEV, generator=g).to(dtype).contiguous(memory_format=CL3)
+    s1 = skip.clone(memory_format=torch.preserve_format).requires_grad_(True)
+    d1 = dec.clone(memory_format=torch.preserve_format).requires_grad_(True) if Cd else None
+    cat = ops.tlerp_cat(d1, s1)
+    vec_ok = Cd % (16 // skip.element_size()) == 0 and Cs % (16 // skip.element_size()) == 0
+    assert cat.is_contiguous(memory_format=CL3) == vec_ok or h == 1
+    cat.backward(gcat)
+    want = torch_ref.tlerp_cat_with_grads(None if dec is None else dec.float(), skip.float(), gcat.float())
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    assert float((cat.detach().float() - want[0]).abs().max()) <= tol
+    assert float((s1.grad.float() - want[2]).abs().max()) <= (2e-6 if dtype == torch.float32 else 4e-2)
+    if Cd:
+        assert torch.equal(d1.grad.float(), want[1])
+    # two channels-last frames (the Siamese backbone's outputs) give the same bits
+    a = skip[:, :, 0].contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    b = skip[:, :, 1].contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    cat2 = ops.tlerp_pair_cat(dec, a, b)
+    cat2.backward(gcat)
+    assert torch.equal(cat2.detach(), cat.detach())
+    assert torch.equal(a.grad, s1.grad[:, :, 0]) and torch.equal(b.grad, s1.grad[:, :, 1])
