@@ -102,6 +102,26 @@ def sweep_warp(args, emit):
                     nb = ops.warp_bwd_bytes(B, C, H, W, s)
                     emit(dict(base, op="warp_stack_bwd", variant=bv, ms=ms, gbps=nb / ms / 1e6,
                               frac=nb / ms / 1e6 / peak(), ref_ms=ref_b, speedup=(ref_b / ms) if ref_b else None))
+                if dtype == torch.float32:      # channels_last_3d tensors -> NDHWC kernels (reported as variant 9)
+                    cl = torch.channels_last_3d
+                    xc = x.contiguous(memory_format=cl)
+                    gc = gout.contiguous(memory_format=cl)
+                    with torch.no_grad():
+                        ms = time_fn(lambda: ops.flow_warp(xc, flow, (H, W)), args.warm, args.iters)
+                    nb = ops.warp_fwd_bytes(B, C, H, W, s)
+                    emit(dict(base, op="warp_stack_fwd", variant=9, ms=ms, gbps=nb / ms / 1e6, frac=nb / ms / 1e6 / peak(),
+                              ref_ms=ref_f, speedup=(ref_f / ms) if ref_f else None))
+                    xcg, fcg = xc.clone(memory_format=torch.preserve_format).requires_grad_(True), flow.clone().requires_grad_(True)
+                    outc = ops.flow_warp(xcg, fcg, (H, W))
+
+                    def bwdc():
+                        xcg.grad = fcg.grad = None
+                        outc.backward(gc, retain_graph=True)
+                    ms = time_fn(bwdc, args.warm, args.iters)
+                    nb = ops.warp_bwd_bytes(B, C, H, W, s)
+                    emit(dict(base, op="warp_stack_bwd", variant=9, ms=ms, gbps=nb / ms / 1e6, frac=nb / ms / 1e6 / peak(),
+                              ref_ms=ref_b, speedup=(ref_b / ms) if ref_b else None))
+                    del xc, gc, xcg, fcg, outc
                 del x, flow, gout, out, xg, fg
                 torch.cuda.empty_cache()
 
@@ -145,6 +165,26 @@ def sweep_tlerp(args, emit):
             nb = ops.tlerp_bwd_bytes(B, Cs, h * h, s)
             emit(dict(base, op="tlerp_cat_bwd", variant=0, ms=ms, gbps=nb / ms / 1e6, frac=nb / ms / 1e6 / peak(),
                       ref_ms=ref_b, speedup=ref_b / ms))
+            cl = torch.channels_last_3d     # channels_last_3d tensors -> NDHWC kernels (variant 9)
+            v = 16 // s
+            if Cd % v == 0 and Cs % v == 0:
+                skc, dc, gc = (t.contiguous(memory_format=cl) for t in (skip, dec, gcat))
+                with torch.no_grad():
+                    ms = time_fn(lambda: ops.tlerp_cat(dc, skc), args.warm, args.iters)
+                nb = ops.tlerp_fwd_bytes(B, Cd, Cs, h * h, s)
+                emit(dict(base, op="tlerp_cat_fwd", variant=9, ms=ms, gbps=nb / ms / 1e6, frac=nb / ms / 1e6 / peak(),
+                          ref_ms=ref_f, speedup=ref_f / ms))
+                sgc = skc.clone(memory_format=torch.preserve_format).requires_grad_(True)
+                catc = ops.tlerp_cat(dc, sgc)
+
+                def bwdc():
+                    sgc.grad = None
+                    catc.backward(gc, retain_graph=True)
+                ms = time_fn(bwdc, args.warm, args.iters)
+                nb = ops.tlerp_bwd_bytes(B, Cs, h * h, s)
+                emit(dict(base, op="tlerp_cat_bwd", variant=9, ms=ms, gbps=nb / ms / 1e6, frac=nb / ms / 1e6 / peak(),
+                          ref_ms=ref_b, speedup=ref_b / ms))
+                del skc, dc, gc, sgc, catc
             del skip, dec, gcat, cat, catr
             torch.cuda.empty_cache()
 

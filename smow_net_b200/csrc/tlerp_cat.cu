@@ -147,44 +147,43 @@ tlerp_cat_bwd_kernel(const T* __restrict__ gcat, T* __restrict__ g1, T* __restri
 // ------------------------------------------------------------------------------
 // channels-last (NDHWC) variants: memory order (B, T, h*w, C); vectors run along C
 // ------------------------------------------------------------------------------
+// One thread per 16-byte vector of the OUTPUT row (b, slot, pixel): consecutive threads write consecutive
+// bytes of cat (the dec part, then the lerped skip part of the same pixel), so every 32-byte sector is completed
+// by one warp even when Cd*sizeof(T) is not a multiple of 32 (SMOW_Net_LW's 28+16 channel level).  The skip
+// vectors are re-read once per slot (4x, from L2/L1 — they are a small fraction of the concat).
 template <typename T>
 __global__ void __launch_bounds__(256)
 tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, const T* __restrict__ s2,
-                           int64_t sB, T* __restrict__ cat, int Cd, int Cs, int64_t hw, int64_t n_lerp,
-                           int64_t n_copy, int lerp_blocks) {
+                           int64_t sB, T* __restrict__ cat, int Cd, int Cs, int64_t hw, int64_t n_items,
+                           bool do_copy, bool do_lerp) {
   constexpr int V = Vec<T>::N;
   const int Ct = Cd + Cs;
-  if ((int)blockIdx.x < lerp_blocks) {
-    const LerpW lw = lerp_weights();
-    const int64_t qs = Cs / V;
-    const bool small = n_lerp < (1ll << 31);
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_lerp; i += (int64_t)lerp_blocks * 256) {
-      int64_t bp, vs, b, p;
-      split_index(i, qs, small, bp, vs);
-      split_index(bp, hw, small, b, p);
-      const T* p1 = s1 + b * sB + p * Cs + vs * V;
-      const T* p2 = s2 + b * sB + p * Cs + vs * V;
-      T* o = cat + ((b * 4) * hw + p) * Ct + Cd + vs * V;
-      const Vec<T> a = ldv(p1), bb = ldv(p2);
-      Vec<T> m1, m2;
+  const int64_t qd = Cd / V, qt = Ct / V;
+  const LerpW lw = lerp_weights();
+  const bool small = n_items < (1ll << 31);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_items; i += (int64_t)gridDim.x * 256) {
+    int64_t r, vt;
+    split_index(i, qt, small, r, vt);          // r = (b*4 + slot)*hw + p
+    if (vt < qd) {
+      if (do_copy) stv(cat + r * Ct + vt * V, ldv_stream(dec + r * Cd + vt * V));
+      continue;
+    }
+    if (!do_lerp) continue;
+    int64_t bs, p;
+    split_index(r, hw, small, bs, p);
+    const int64_t b = bs >> 2;
+    const int slot = (int)(bs & 3);
+    const int64_t off = b * sB + p * Cs + (vt - qd) * V;
+    Vec<T> o;
+    if (slot == 0) o = ldv(s1 + off);
+    else if (slot == 3) o = ldv(s2 + off);
+    else {
+      const Vec<T> a = ldv(s1 + off), bb = ldv(s2 + off);
+      const float wa = slot == 1 ? lw.a1 : lw.a2, wb = slot == 1 ? lw.b1 : lw.b2;
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const float fa = cvtf<T>(a.v[j]), fb = cvtf<T>(bb.v[j]);
-        m1.v[j] = fromf<T>(fmaf(lw.a1, fa, __fmul_rn(lw.b1, fb)));
-        m2.v[j] = fromf<T>(fmaf(lw.a2, fa, __fmul_rn(lw.b2, fb)));
-      }
-      const int64_t fs = hw * Ct;    // frame stride of cat
-      stv(o, a); stv(o + fs, m1); stv(o + 2 * fs, m2); stv(o + 3 * fs, bb);
+      for (int j = 0; j < V; ++j) o.v[j] = fromf<T>(fmaf(wa, cvtf<T>(a.v[j]), __fmul_rn(wb, cvtf<T>(bb.v[j]))));
     }
-  } else {
-    const int cb = (int)gridDim.x - lerp_blocks;
-    const int64_t qd = Cd / V;
-    const bool small = n_copy < (1ll << 31);
-    for (int64_t i = (int64_t)(blockIdx.x - lerp_blocks) * 256 + threadIdx.x; i < n_copy; i += (int64_t)cb * 256) {
-      int64_t r, vd;
-      split_index(i, qd, small, r, vd);        // r = (b*4 + slot)*hw + p
-      stv(cat + r * Ct + vd * V, ldv_stream(dec + r * Cd + vd * V));
-    }
+    stv(cat + r * Ct + vt * V, o);
   }
 }
 
@@ -266,12 +265,10 @@ static int fwd_ndhwc(const T* dec, const T* s1, const T* s2, int64_t sB, T* cat,
   if (Cd % V || Cs % V || !aligned16(cat) || (do_lerp && (!aligned16(s1) || !aligned16(s2) || sB % V)) ||
       (do_copy && !aligned16(dec)))
     return fail(SMOW_EALIGN, "tlerp_cat NDHWC needs Cd, Cs multiples of %d and 16 B aligned tensors", V);
-  const int64_t n_lerp = do_lerp ? (int64_t)B * hw * (Cs / V) : 0;
-  const int64_t n_copy = do_copy ? (int64_t)B * 4 * hw * (Cd / V) : 0;
+  const int64_t n_items = (int64_t)B * 4 * hw * ((Cd + Cs) / V);
   const int cap = device_info().sms * 8;
-  const int lb = (int)((n_lerp + 255) / 256 < cap ? (n_lerp + 255) / 256 : cap);
-  const int cb = (int)((n_copy + 511) / 512 < cap ? (n_copy + 511) / 512 : cap);
-  tlerp_cat_fwd_ndhwc_kernel<T><<<lb + cb, 256, 0, st>>>(dec, s1, s2, sB, cat, Cd, Cs, hw, n_lerp, n_copy, lb);
+  const int nb = (int)((n_items + 255) / 256 < cap ? (n_items + 255) / 256 : cap);
+  tlerp_cat_fwd_ndhwc_kernel<T><<<nb, 256, 0, st>>>(dec, s1, s2, sB, cat, Cd, Cs, hw, n_items, do_copy, do_lerp);
   count_launch();
   return check_launch("tlerp_cat_fwd (NDHWC)");
 }

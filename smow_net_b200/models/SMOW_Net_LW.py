@@ -48,7 +48,13 @@ class SMOW_Net_LW(nn.Module):
         pyr1 = self.backbone(x1)                                # 5 levels, T1
         pyr2 = self.backbone(x2)                                # same weights, T2
 
-        x0 = torch.stack((pyr1[0], pyr2[0]), dim=2).contiguous()   # (B,16,2,H/2,W/2), reference :38-40
+        # (B,16,2,H/2,W/2), reference :38-40 — stacked straight into channels_last_3d on the GPU so that OFW's
+        # convolutions and the warp kernels all see NDHWC
+        x0 = torch.empty((pyr1[0].shape[0], pyr1[0].shape[1], 2) + tuple(pyr1[0].shape[2:]), dtype=pyr1[0].dtype,
+                         device=pyr1[0].device,
+                         memory_format=torch.channels_last_3d if x1.is_cuda else torch.contiguous_format)
+        x0[:, :, 0] = pyr1[0]
+        x0[:, :, 1] = pyr2[0]
         tokens = self.Transformer_Encoder(self.OFW(x0))
 
         dec = self.MaxPool(ops.tlerp_pair_cat(None, pyr1[4], pyr2[4]))   # reference :71-73
