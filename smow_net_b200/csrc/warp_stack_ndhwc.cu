@@ -158,14 +158,20 @@ warp_bwd_ndhwc_scatter_kernel(const float* __restrict__ gout, const float* __res
     mx = __fmul_rn(fp.gx_gate, __fmul_rn((float)(W - 1), 0.5f));
     my = __fmul_rn(fp.gy_gate, __fmul_rn((float)(H - 1), 0.5f));
   }
-  if (shuffle_reduce) {      // the q lanes of a pixel are adjacent and q divides 32: butterfly over them
-    for (int d = q >> 1; d > 0; d >>= 1) {
+  if (shuffle_reduce) {      // q is a power of two: the lanes of a pixel are adjacent, butterfly over min(q, 32) of them
+    const int span = q < 32 ? q : 32;
+    for (int d = span >> 1; d > 0; d >>= 1) {
       gix += __shfl_xor_sync(0xffffffffu, gix, d);
       giy += __shfl_xor_sync(0xffffffffu, giy, d);
     }
-    if (live && v == 0) {
-      gflow[fo] = __fdiv_rn(__fmul_rn(mx, gix), (float)W);
-      gflow[fo + 2 * (int64_t)HW] = __fdiv_rn(__fmul_rn(my, giy), (float)H);
+    if (live && (v & (span - 1)) == 0) {
+      if (q <= 32) {
+        gflow[fo] = __fdiv_rn(__fmul_rn(mx, gix), (float)W);
+        gflow[fo + 2 * (int64_t)HW] = __fdiv_rn(__fmul_rn(my, giy), (float)H);
+      } else {               // several warps share a pixel: one atomic per warp into the zeroed gradient
+        atomicAdd(gflow + fo, __fdiv_rn(__fmul_rn(mx, gix), (float)W));
+        atomicAdd(gflow + fo + 2 * (int64_t)HW, __fdiv_rn(__fmul_rn(my, giy), (float)H));
+      }
     }
   } else if (live) {
     atomicAdd(gflow + fo, __fdiv_rn(__fmul_rn(mx, gix), (float)W));
@@ -203,9 +209,9 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
       return fail(SMOW_EALIGN, "NDHWC warp needs C %% 4 == 0 and 16 B aligned tensors");
     const int q = C / 4, qs = ilog2_exact(q);
     if ((int64_t)H * W * q >= (1ll << 31)) return fail(SMOW_ERANGE, "plane too large");
-    const bool shuffle = qs >= 0 && q <= 32;
+    const bool shuffle = qs >= 0;
     dim3 grid((unsigned)(((int64_t)H * W * q + 255) / 256), 2 * B);
-    warp_bwd_ndhwc_init_kernel<float><<<grid, 256, 0, st>>>(gout, gx1, gx2, sB, gflow, C, H * W, q, !shuffle);
+    warp_bwd_ndhwc_init_kernel<float><<<grid, 256, 0, st>>>(gout, gx1, gx2, sB, gflow, C, H * W, q, !shuffle || q > 32);
     warp_bwd_ndhwc_scatter_kernel<<<grid, 256, 0, st>>>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, C, H, W, q, qs,
                                                         shuffle);
     count_launch(2);
