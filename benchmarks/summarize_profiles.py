@@ -164,7 +164,7 @@ def sweep(tag):
         f.write("`python benchmarks/sweep_warp.py --iters 10`; working set >= 1 GiB per launch (HBM-cold). GB/s = ALGORITHMIC bytes\n"
                 "(SURVEY §8(d)) / time; frac = of the measured copy bandwidth (MEASURED_PEAKS.json, 6547.8 GB/s); ref = the reference's\n"
                 "own op sequence (F.grid_sample + cat / F.interpolate + cat, ATen sm_100 kernels) on the same GPU.\n"
-                "variant: 0 direct / atomics, 1 bulk-copy staged planes, 2 channel-vectorised tiles.\n\n")
+                "variant: 0 direct / atomics, 1 bulk-copy staged planes, 2 channel-vectorised tiles, 9 NDHWC (channels_last_3d) kernels.\n\n")
         f.write("| op | dtype | C | H=W | B | sigma | variant | ms | GB/s | frac | ref ms | speed-up |\n|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
         for r in rows:
             if not r["op"].startswith("warp"):
@@ -172,12 +172,12 @@ def sweep(tag):
             f.write("| %s | %s | %d | %d | %d | %.1f | %d | %.3f | %.0f | %.2f | %s | %s |\n" % (
                 r["op"], r["dtype"], r["C"], r["H"], r["B"], r["sigma"], r["variant"], r["ms"], r["gbps"], r["frac"],
                 "%.3f" % r["ref_ms"] if r["ref_ms"] else "-", "%.1fx" % r["speedup"] if r["speedup"] else "-"))
-        f.write("\n| op | dtype | Cd | Cs | h=w | B | ms | GB/s | frac | ref ms | speed-up |\n|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        f.write("\n| op | dtype | Cd | Cs | h=w | B | variant | ms | GB/s | frac | ref ms | speed-up |\n|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
         for r in rows:
             if r["op"].startswith("warp"):
                 continue
-            f.write("| %s | %s | %d | %d | %d | %d | %.3f | %.0f | %.2f | %.3f | %.1fx |\n" % (
-                r["op"], r["dtype"], r["Cd"], r["Cs"], r["h"], r["B"], r["ms"], r["gbps"], r["frac"], r["ref_ms"], r["speedup"]))
+            f.write("| %s | %s | %d | %d | %d | %d | %d | %.3f | %.0f | %.2f | %.3f | %.1fx |\n" % (
+                r["op"], r["dtype"], r["Cd"], r["Cs"], r["h"], r["B"], r["variant"], r["ms"], r["gbps"], r["frac"], r["ref_ms"], r["speedup"]))
 
 
 if __name__ == "__main__":
