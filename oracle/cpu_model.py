@@ -40,6 +40,9 @@ def time_cpu_fwd_bwd(kind, batch, steps, warmup, budget_s=150.0, threads=None):
     with reference_ops():
         torch.manual_seed(2022)
         model = build_model(kind, torch.device("cpu")).train()
+        for prm in model.parameters():          # the reference keeps its weights in the default (contiguous) order
+            if prm.dim() >= 4:
+                prm.data = prm.data.contiguous()
         a, b, y = synthetic.make_batch(batch)
         t0 = time.perf_counter()
         S.fwd_bwd(model, a, b, y)                     # first (untimed) step doubles as the probe
