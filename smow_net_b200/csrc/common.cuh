@@ -97,6 +97,39 @@ __device__ __forceinline__ Footprint footprint(float xs_w, float ys_h, float fx,
   return f;
 }
 
+// Same chain with the division by a power-of-two size done as an exact multiplication by 2^-k
+// (bit-identical result, ~20 instructions shorter than the IEEE division sequence).
+__device__ __forceinline__ Axis axis_coord_pow2(float base, float flow, int size, float inv) {
+  float g = __fadd_rn(base, __fmul_rn(flow, inv));
+  const bool pass_clamp = (g >= -1.f) && (g <= 1.f);
+  g = fminf(fmaxf(g, -1.f), 1.f);
+  const float hi = (float)(size - 1);
+  float i = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), hi);
+  const bool pass_clip = (i > 0.f) && (i < hi);
+  i = fminf(hi, fmaxf(i, 0.f));
+  Axis a;
+  a.i = i; a.i0f = floorf(i); a.i0 = (int)a.i0f;
+  a.gmult = (pass_clamp && pass_clip) ? 1.f : 0.f;
+  return a;
+}
+
+// footprint() with the power-of-two shortcut taken per axis when the size allows it (uniform branch)
+__device__ __forceinline__ Footprint footprint_auto(float xs_w, float ys_h, float fx, float fy, int W, int H) {
+  const bool wp = (W & (W - 1)) == 0, hp = (H & (H - 1)) == 0;
+  const Axis ax = wp ? axis_coord_pow2(xs_w, fx, W, 1.f / (float)W) : axis_coord(xs_w, fx, W);
+  const Axis ay = hp ? axis_coord_pow2(ys_h, fy, H, 1.f / (float)H) : axis_coord(ys_h, fy, H);
+  Footprint f;
+  f.x0 = ax.i0; f.y0 = ay.i0;
+  f.wx0 = __fsub_rn(__fadd_rn(ax.i0f, 1.f), ax.i);
+  f.wx1 = __fsub_rn(ax.i, ax.i0f);
+  f.wy0 = __fsub_rn(__fadd_rn(ay.i0f, 1.f), ay.i);
+  f.wy1 = __fsub_rn(ay.i, ay.i0f);
+  f.x1ok = (ax.i0 + 1) <= (W - 1);
+  f.y1ok = (ay.i0 + 1) <= (H - 1);
+  f.gx_gate = ax.gmult; f.gy_gate = ay.gmult;
+  return f;
+}
+
 // temporal lerp weights of upsample_trilinear3d(2 -> 4, align_corners=True):
 // rdepth = (2-1)/(4-1) as fp32; t1lambda = rdepth * t2 - floor(.)
 #define SMOW_LAMBDA1 0.3333333432674408f

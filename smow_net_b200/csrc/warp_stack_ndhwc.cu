@@ -73,7 +73,7 @@ warp_fwd_ndhwc_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int64_
   const int b = blockIdx.y >> 1, t = blockIdx.y & 1;
   const int h = p / W, w = p - h * W;
   const int64_t fo = ((int64_t)(b * 2) * 2 + t) * HW + p;
-  const Footprint fp = footprint(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
+  const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
   const float nw = __fmul_rn(fp.wx0, fp.wy0), ne = __fmul_rn(fp.wx1, fp.wy0);
   const float sw = __fmul_rn(fp.wx0, fp.wy1), se = __fmul_rn(fp.wx1, fp.wy1);
   const T* src = (t ? x2 : x1) + b * sB + v * V;
@@ -137,7 +137,7 @@ warp_bwd_ndhwc_scatter_kernel(const float* __restrict__ gout, const float* __res
   if (live) {
     const int h = p / W, w = p - h * W;
     fo = ((int64_t)(b * 2) * 2 + t) * HW + p;
-    const Footprint fp = footprint(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
+    const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
     const float nw = __fmul_rn(fp.wx0, fp.wy0), ne = __fmul_rn(fp.wx1, fp.wy0);
     const float sw = __fmul_rn(fp.wx0, fp.wy1), se = __fmul_rn(fp.wx1, fp.wy1);
     const float4 g = __ldg(reinterpret_cast<const float4*>(gout + ((int64_t)(b * 4 + 1 + t) * HW + p) * C + v * 4));
