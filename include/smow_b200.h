@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SMOW_ABI_VERSION 1
+#define SMOW_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SMOW_API __attribute__((visibility("default")))
@@ -95,18 +95,24 @@ SMOW_API int smow_warp_pair_fwd(const void* x_t1, const void* x_t2, const float*
  *   gx[:,:,0] = gout[:,:,0] + scatter(gout[:,:,1]);  gx[:,:,1] = gout[:,:,3] + scatter(gout[:,:,2])
  *   gflow     = d(out)/d(flow) with the clamp mask (inclusive at ±1) and the
  *               border-clip mask.  gx needs no zero-fill by the caller.
- *   gout (B,C,4,H,W)  x (B,C,2,H,W)  gx (B,C,2,H,W)  gflow (B,2,2,H,W) fp32      */
+ *   gout (B,C,4,H,W)  x (B,C,2,H,W)  gx (B,C,2,H,W)  gflow (B,2,2,H,W) fp32
+ * workspace: optional caller-owned device scratch of at least smow_warp_bwd_workspace_bytes(B,H,W)
+ *   bytes (uninitialised is fine; may be NULL).  With it the fp32 NDHWC backward runs as a
+ *   deterministic gather (sample coordinates of every pixel are staged there once); without
+ *   it, or when the flow's displacement range is too wide for the gather window, the vector-atomic
+ *   scatter is used.  The library still never allocates.                                   */
+SMOW_API int64_t smow_warp_bwd_workspace_bytes(int B, int H, int W);
 SMOW_API int smow_warp_stack_bwd(const void* gout, const void* x, const float* flow,
                         const float* xs, const float* ys,
                         void* gx, float* gflow,
                         int B, int C, int H, int W,
-                        int dtype, int layout, void* stream);
+                        int dtype, int layout, void* workspace, int64_t workspace_bytes, void* stream);
 
 SMOW_API int smow_warp_pair_bwd(const void* gout, const void* x_t1, const void* x_t2,
                        const float* flow, const float* xs, const float* ys,
                        void* gx_t1, void* gx_t2, float* gflow,
                        int B, int C, int H, int W,
-                       int dtype, int layout, void* stream);
+                       int dtype, int layout, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- A3+A4: temporal 2→4 lerp written straight into the decoder concat ----------
  * Replaces F.interpolate(xk, size=(4,h,w), 'trilinear', align_corners=True)

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmow_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 F32, BF16 = 0, 1
 NCDHW, NDHWC = 0, 1
 
@@ -24,8 +24,9 @@ SIGNATURES = {
     "smow_get_option": (_i, [ctypes.c_char_p]),
     "smow_warp_stack_fwd": (_i, [_vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "smow_warp_pair_fwd": (_i, [_vp, _vp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "smow_warp_stack_bwd": (_i, [_vp, _vp, _fp, _fp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
-    "smow_warp_pair_bwd": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
+    "smow_warp_bwd_workspace_bytes": (_i64, [_i, _i, _i]),
+    "smow_warp_stack_bwd": (_i, [_vp, _vp, _fp, _fp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "smow_warp_pair_bwd": (_i, [_vp, _vp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
     "smow_tlerp_cat_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _vp]),
     "smow_tlerp_pair_cat_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _vp]),
     "smow_tlerp_cat_bwd": (_i, [_vp, _vp, _i, _i, _i, _i64, _i, _i, _vp]),

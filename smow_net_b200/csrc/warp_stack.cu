@@ -183,9 +183,9 @@ template <typename T>
 static int bwd_impl(const T* gout, const T* x1, const T* x2, int64_t sB, int64_t sC,
                     const float* flow, const float* xs, const float* ys,
                     T* gx1, T* gx2, float* gflow, int B, int C, int H, int W,
-                    int layout, cudaStream_t st) {
+                    int layout, void* ws, int64_t ws_bytes, cudaStream_t st) {
   if (layout == SMOW_NDHWC)
-    return warp_bwd_ndhwc<T>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, st);
+    return warp_bwd_ndhwc<T>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, ws, ws_bytes, st);
   int variant = option(OPT_WARP_BWD_VARIANT);
   if (variant < -1 || variant > 2) return fail(SMOW_EINVAL, "unknown warp_bwd_variant %d", variant);
   if (variant == -1) variant = 2;   // falls through to 1 for bf16 / uncovered shapes, then to 0
@@ -216,6 +216,11 @@ static int bwd_impl(const T* gout, const T* x1, const T* x2, int64_t sB, int64_t
 using namespace smow;
 
 extern "C" {
+
+int64_t smow_warp_bwd_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return 64 + (int64_t)B * 2 * 2 * H * W * (int64_t)sizeof(float);   // header + (ix, iy) of every pixel-frame
+}
 
 int smow_warp_pair_fwd(const void* x_t1, const void* x_t2, const float* flow, const float* xs,
                        const float* ys, void* out, int B, int C, int H, int W, int dtype, int layout,
@@ -251,22 +256,24 @@ int smow_warp_stack_fwd(const void* x, const float* flow, const float* xs, const
 
 int smow_warp_pair_bwd(const void* gout, const void* x_t1, const void* x_t2, const float* flow,
                        const float* xs, const float* ys, void* gx_t1, void* gx_t2, float* gflow, int B,
-                       int C, int H, int W, int dtype, int layout, void* stream) {
+                       int C, int H, int W, int dtype, int layout, void* workspace, int64_t workspace_bytes,
+                       void* stream) {
   if (!x_t2 || !gx_t2 || !gflow || !xs || !ys || !flow) return fail(SMOW_EINVAL, "null pointer argument");
   if (int e = check_common(gout, x_t1, gx_t1, gflow, B, C, H, W, dtype, layout)) return e;
   const int64_t HW = (int64_t)H * W;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == SMOW_F32)
     return bwd_impl<float>((const float*)gout, (const float*)x_t1, (const float*)x_t2, C * HW, HW, flow,
-                           xs, ys, (float*)gx_t1, (float*)gx_t2, gflow, B, C, H, W, layout, st);
+                           xs, ys, (float*)gx_t1, (float*)gx_t2, gflow, B, C, H, W, layout, workspace, workspace_bytes, st);
   return bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)gout, (const __nv_bfloat16*)x_t1,
                                  (const __nv_bfloat16*)x_t2, C * HW, HW, flow, xs, ys,
-                                 (__nv_bfloat16*)gx_t1, (__nv_bfloat16*)gx_t2, gflow, B, C, H, W, layout, st);
+                                 (__nv_bfloat16*)gx_t1, (__nv_bfloat16*)gx_t2, gflow, B, C, H, W, layout, workspace,
+                                 workspace_bytes, st);
 }
 
 int smow_warp_stack_bwd(const void* gout, const void* x, const float* flow, const float* xs,
                         const float* ys, void* gx, float* gflow, int B, int C, int H, int W, int dtype,
-                        int layout, void* stream) {
+                        int layout, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!gflow || !xs || !ys || !flow) return fail(SMOW_EINVAL, "null pointer argument");
   if (int e = check_common(gout, x, gx, gflow, B, C, H, W, dtype, layout)) return e;
   const int64_t HW = (int64_t)H * W;
@@ -276,12 +283,12 @@ int smow_warp_stack_bwd(const void* gout, const void* x, const float* flow, cons
     const float* p = (const float*)x;
     float* q = (float*)gx;
     return bwd_impl<float>((const float*)gout, p, p + fs, 2 * C * HW, 2 * HW, flow, xs, ys, q, q + fs, gflow,
-                           B, C, H, W, layout, st);
+                           B, C, H, W, layout, workspace, workspace_bytes, st);
   }
   const __nv_bfloat16* p = (const __nv_bfloat16*)x;
   __nv_bfloat16* q = (__nv_bfloat16*)gx;
   return bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)gout, p, p + fs, 2 * C * HW, 2 * HW, flow, xs, ys, q,
-                                 q + fs, gflow, B, C, H, W, layout, st);
+                                 q + fs, gflow, B, C, H, W, layout, workspace, workspace_bytes, st);
 }
 
 }  // extern "C"

@@ -107,8 +107,19 @@ warp_fwd_ndhwc_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int64_
 template <typename T>
 __global__ void __launch_bounds__(256)
 warp_bwd_ndhwc_init_kernel(const T* __restrict__ gout, T* __restrict__ gx1, T* __restrict__ gx2, int64_t sB,
-                           float* __restrict__ gflow, int C, int HW, int q, bool zero_gflow) {
+                           float* __restrict__ gflow, int C, int HW, int q, bool zero_gflow, const int* __restrict__ hdr) {
   constexpr int V = CVec<T>::N;
+  if (hdr != nullptr) {               // gather mode: only the (rare, wide-C) atomic flow-gradient needs zeroing
+    const int nx = hdr[1] - hdr[0] + 2, ny = hdr[3] - hdr[2] + 2;
+    if (nx > 0 && ny > 0 && nx * ny <= 49) {
+      const int i = blockIdx.x * 256 + threadIdx.x;
+      if (zero_gflow && i < HW) {
+        const int64_t fo = ((int64_t)((blockIdx.y >> 1) * 2) * 2 + (blockIdx.y & 1)) * HW + i;
+        gflow[fo] = 0.f; gflow[fo + 2 * (int64_t)HW] = 0.f;
+      }
+      return;
+    }
+  }
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= HW * q) return;
   const int b = blockIdx.y >> 1, t = blockIdx.y & 1;
@@ -125,7 +136,12 @@ __global__ void __launch_bounds__(256)
 warp_bwd_ndhwc_scatter_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
                               int64_t sB, const float* __restrict__ flow, const float* __restrict__ xs,
                               const float* __restrict__ ys, float* __restrict__ gx1, float* __restrict__ gx2,
-                              float* __restrict__ gflow, int C, int H, int W, int q, int qshift, bool shuffle_reduce) {
+                              float* __restrict__ gflow, int C, int H, int W, int q, int qshift, bool shuffle_reduce,
+                              const int* __restrict__ hdr) {
+  if (hdr != nullptr) {               // the gather kernel already produced this launch's gradients
+    const int nx = hdr[1] - hdr[0] + 2, ny = hdr[3] - hdr[2] + 2;
+    if (nx > 0 && ny > 0 && nx * ny <= 49) return;
+  }
   const int HW = H * W;
   const int idx = blockIdx.x * 256 + threadIdx.x;
   const bool live = idx < HW * q;
@@ -179,6 +195,135 @@ warp_bwd_ndhwc_scatter_kernel(const float* __restrict__ gout, const float* __res
   }
 }
 
+
+// ------------------------------------------------------------------------------
+// deterministic gather backward (needs the caller's workspace)
+// ------------------------------------------------------------------------------
+// workspace: [0..3] int header {dxmin, dxmax, dymin, dymax} = range of the integer displacement
+// (anchor - pixel) over the whole launch, then two float planes (ix, iy) of B*2*HW clipped sample coordinates.
+constexpr int GATHER_MAX_WINDOW = 49;     // candidates per target beyond which the atomic scatter takes over
+
+__device__ __forceinline__ bool gather_enabled(const int* hdr) {
+  const int nx = hdr[1] - hdr[0] + 2, ny = hdr[3] - hdr[2] + 2;
+  return nx > 0 && ny > 0 && nx * ny <= GATHER_MAX_WINDOW;
+}
+
+__global__ void warp_bwd_ndhwc_hdr_kernel(int* hdr) {
+  if (threadIdx.x < 4) hdr[threadIdx.x] = (threadIdx.x & 1) ? -(1 << 30) : (1 << 30);
+}
+
+__global__ void __launch_bounds__(256)
+warp_bwd_ndhwc_stat_kernel(const float* __restrict__ flow, const float* __restrict__ xs, const float* __restrict__ ys,
+                           int* __restrict__ hdr, float* __restrict__ cix, float* __restrict__ ciy, int H, int W) {
+  __shared__ int red[4];
+  const int HW = H * W;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int b = blockIdx.y >> 1, t = blockIdx.y & 1;
+  if (threadIdx.x < 4) red[threadIdx.x] = (threadIdx.x & 1) ? -(1 << 30) : (1 << 30);
+  __syncthreads();
+  int dx0 = 1 << 30, dx1 = -(1 << 30), dy0 = 1 << 30, dy1 = -(1 << 30);
+  if (p < HW) {
+    const int h = p / W, w = p - h * W;
+    const int64_t fo = ((int64_t)(b * 2) * 2 + t) * HW + p;
+    const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
+    const int64_t o = (int64_t)(b * 2 + t) * HW + p;
+    cix[o] = __fadd_rn((float)fp.x0, fp.wx1);          // = ix exactly (wx1 = ix - floor(ix))
+    ciy[o] = __fadd_rn((float)fp.y0, fp.wy1);
+    dx0 = dx1 = fp.x0 - w; dy0 = dy1 = fp.y0 - h;
+  }
+  dx0 = __reduce_min_sync(0xffffffffu, dx0); dx1 = __reduce_max_sync(0xffffffffu, dx1);
+  dy0 = __reduce_min_sync(0xffffffffu, dy0); dy1 = __reduce_max_sync(0xffffffffu, dy1);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(red + 0, dx0); atomicMax(red + 1, dx1); atomicMin(red + 2, dy0); atomicMax(red + 3, dy1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicMin(hdr + 0, red[0]); atomicMax(hdr + 1, red[1]); atomicMin(hdr + 2, red[2]); atomicMax(hdr + 3, red[3]);
+  }
+}
+
+// thread = (pixel, 4-channel vector).  Target side: gx = gout[pass] + sum over the sources whose bilinear
+// footprint covers this pixel (found by scanning the coordinate planes in a fixed order: bit-reproducible);
+// source side: flow-gradient sums of this pixel's own footprint, combined over the lanes of the pixel.
+__global__ void __launch_bounds__(256)
+warp_bwd_ndhwc_gather_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
+                             int64_t sB, const float* __restrict__ flow, const float* __restrict__ xs,
+                             const float* __restrict__ ys, const int* __restrict__ hdr, const float* __restrict__ cix,
+                             const float* __restrict__ ciy, float* __restrict__ gx1, float* __restrict__ gx2,
+                             float* __restrict__ gflow, int C, int H, int W, int q, int qshift) {
+  if (!gather_enabled(hdr)) return;                       // the atomic scatter kernels handle this launch
+  const int dxlo = hdr[0], dxhi = hdr[1], dylo = hdr[2], dyhi = hdr[3];
+  const int HW = H * W;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const bool live = idx < HW * q;
+  int p = 0, v = 0;
+  if (live) split_item(idx, q, qshift, p, v);
+  const int b = blockIdx.y >> 1, t = blockIdx.y & 1;
+  float gix = 0.f, giy = 0.f, mx = 0.f, my = 0.f;
+  int64_t fo = 0;
+  if (live) {
+    const int h = p / W, w = p - h * W;
+    fo = ((int64_t)(b * 2) * 2 + t) * HW + p;
+    const float* gw = gout + ((int64_t)(b * 4 + 1 + t) * HW) * C + v * 4;      // warped-slot gradient plane
+    // ---- target side ----
+    float4 acc = __ldg(reinterpret_cast<const float4*>(gout + ((int64_t)(b * 4 + (t ? 3 : 0)) * HW + p) * C + v * 4));
+    const float* px = cix + (int64_t)(b * 2 + t) * HW;
+    const float* py = ciy + (int64_t)(b * 2 + t) * HW;
+    const int sy_a = max(0, h - 1 - dyhi), sy_b = min(H - 1, h - dylo);
+    const int sx_a = max(0, w - 1 - dxhi), sx_b = min(W - 1, w - dxlo);
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sy = sy_a; sy <= sy_b; ++sy) {
+      for (int sx = sx_a; sx <= sx_b; ++sx) {
+        const int s = sy * W + sx;
+        const float ix = __ldg(px + s), iy = __ldg(py + s);
+        const float x0f = floorf(ix), y0f = floorf(iy);
+        const unsigned ex = (unsigned)(w - (int)x0f), ey = (unsigned)(h - (int)y0f);
+        if ((ex | ey) > 1u) continue;
+        const float wx = ex ? __fsub_rn(ix, x0f) : __fsub_rn(__fadd_rn(x0f, 1.f), ix);
+        const float wy = ey ? __fsub_rn(iy, y0f) : __fsub_rn(__fadd_rn(y0f, 1.f), iy);
+        const float wgt = __fmul_rn(wx, wy);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gw + (int64_t)s * C));
+        sum.x = fmaf(wgt, g.x, sum.x); sum.y = fmaf(wgt, g.y, sum.y);
+        sum.z = fmaf(wgt, g.z, sum.z); sum.w = fmaf(wgt, g.w, sum.w);
+      }
+    }
+    acc.x = __fadd_rn(acc.x, sum.x); acc.y = __fadd_rn(acc.y, sum.y);
+    acc.z = __fadd_rn(acc.z, sum.z); acc.w = __fadd_rn(acc.w, sum.w);
+    *reinterpret_cast<float4*>((t ? gx2 : gx1) + b * sB + (int64_t)p * C + v * 4) = acc;
+    // ---- source side ----
+    const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gw + (int64_t)p * C));
+    const int o_nw = fp.y0 * W + fp.x0;
+    const float* src = (t ? x2 : x1) + b * sB + v * 4;
+    auto tap = [&](int off, float dgx, float dgy) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(src + (int64_t)off * C));
+      const float dot = fmaf(xv.w, g.w, fmaf(xv.z, g.z, fmaf(xv.y, g.y, __fmul_rn(xv.x, g.x))));
+      gix = fmaf(dgx, dot, gix);
+      giy = fmaf(dgy, dot, giy);
+    };
+    tap(o_nw, -fp.wy0, -fp.wx0);
+    if (fp.x1ok) tap(o_nw + 1, fp.wy0, -fp.wx1);
+    if (fp.y1ok) tap(o_nw + W, -fp.wy1, fp.wx0);
+    if (fp.x1ok && fp.y1ok) tap(o_nw + W + 1, fp.wy1, fp.wx1);
+    mx = __fmul_rn(fp.gx_gate, __fmul_rn((float)(W - 1), 0.5f));
+    my = __fmul_rn(fp.gy_gate, __fmul_rn((float)(H - 1), 0.5f));
+  }
+  const int span = q < 32 ? q : 32;       // q is a power of two here (checked by the host)
+  for (int d = span >> 1; d > 0; d >>= 1) {
+    gix += __shfl_xor_sync(0xffffffffu, gix, d);
+    giy += __shfl_xor_sync(0xffffffffu, giy, d);
+  }
+  if (live && (v & (span - 1)) == 0) {
+    if (q <= 32) {
+      gflow[fo] = __fdiv_rn(__fmul_rn(mx, gix), (float)W);
+      gflow[fo + 2 * (int64_t)HW] = __fdiv_rn(__fmul_rn(my, giy), (float)H);
+    } else {
+      atomicAdd(gflow + fo, __fdiv_rn(__fmul_rn(mx, gix), (float)W));
+      atomicAdd(gflow + fo + 2 * (int64_t)HW, __fdiv_rn(__fmul_rn(my, giy), (float)H));
+    }
+  }
+}
+
 static int ilog2_exact(int q) {
   for (int s = 0; s < 31; ++s)
     if ((1 << s) == q) return s;
@@ -201,7 +346,8 @@ int warp_fwd_ndhwc(const T* x1, const T* x2, int64_t sB, const float* flow, cons
 
 template <typename T>
 int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const float* flow, const float* xs,
-                   const float* ys, T* gx1, T* gx2, float* gflow, int B, int C, int H, int W, cudaStream_t st) {
+                   const float* ys, T* gx1, T* gx2, float* gflow, int B, int C, int H, int W, void* ws,
+                   int64_t ws_bytes, cudaStream_t st) {
   if constexpr (!std::is_same<T, float>::value) {
     return fail(SMOW_EDTYPE, "NDHWC warp backward is built for fp32 only (use the NCDHW layout for bf16)");
   } else {
@@ -210,11 +356,26 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
     const int q = C / 4, qs = ilog2_exact(q);
     if ((int64_t)H * W * q >= (1ll << 31)) return fail(SMOW_ERANGE, "plane too large");
     const bool shuffle = qs >= 0;
-    dim3 grid((unsigned)(((int64_t)H * W * q + 255) / 256), 2 * B);
-    warp_bwd_ndhwc_init_kernel<float><<<grid, 256, 0, st>>>(gout, gx1, gx2, sB, gflow, C, H * W, q, !shuffle || q > 32);
+    const int HW = H * W;
+    dim3 grid((unsigned)(((int64_t)HW * q + 255) / 256), 2 * B);
+    // deterministic gather when the caller lent a workspace (and the lanes of a pixel can be shuffle-reduced)
+    const int64_t need = 64 + (int64_t)B * 2 * 2 * HW * (int64_t)sizeof(float);
+    int* hdr = nullptr;
+    int launches = 2;
+    if (ws != nullptr && ws_bytes >= need && shuffle && q <= 32 && aligned16(ws) && option(OPT_WARP_BWD_VARIANT) != 0) {
+      hdr = reinterpret_cast<int*>(ws);
+      float* cix = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 64);
+      float* ciy = cix + (int64_t)B * 2 * HW;
+      warp_bwd_ndhwc_hdr_kernel<<<1, 32, 0, st>>>(hdr);   // min/max sentinels
+      warp_bwd_ndhwc_stat_kernel<<<dim3((HW + 255) / 256, 2 * B), 256, 0, st>>>(flow, xs, ys, hdr, cix, ciy, H, W);
+      warp_bwd_ndhwc_gather_kernel<<<grid, 256, 0, st>>>(gout, x1, x2, sB, flow, xs, ys, hdr, cix, ciy, gx1, gx2, gflow,
+                                                         C, H, W, q, qs);
+      launches += 3;
+    }
+    warp_bwd_ndhwc_init_kernel<float><<<grid, 256, 0, st>>>(gout, gx1, gx2, sB, gflow, C, HW, q, !shuffle || q > 32, hdr);
     warp_bwd_ndhwc_scatter_kernel<<<grid, 256, 0, st>>>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, C, H, W, q, qs,
-                                                        shuffle);
-    count_launch(2);
+                                                        shuffle, hdr);
+    count_launch(launches);
     return check_launch("warp_bwd_ndhwc");
   }
 }
@@ -223,7 +384,7 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
   template int warp_fwd_ndhwc<T>(const T*, const T*, int64_t, const float*, const float*, const float*, T*, \
                                  int, int, int, int, cudaStream_t);                                         \
   template int warp_bwd_ndhwc<T>(const T*, const T*, const T*, int64_t, const float*, const float*,         \
-                                 const float*, T*, T*, float*, int, int, int, int, cudaStream_t);
+                                 const float*, T*, T*, float*, int, int, int, int, void*, int64_t, cudaStream_t);
 INST(float)
 INST(__nv_bfloat16)
 }  // namespace smow

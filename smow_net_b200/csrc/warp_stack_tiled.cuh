@@ -230,6 +230,7 @@ int warp_fwd_ndhwc(const T* x1, const T* x2, int64_t sB, const float* flow, cons
                    T* out, int B, int C, int H, int W, cudaStream_t st);
 template <typename T>
 int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const float* flow, const float* xs,
-                   const float* ys, T* gx1, T* gx2, float* gflow, int B, int C, int H, int W, cudaStream_t st);
+                   const float* ys, T* gx1, T* gx2, float* gflow, int B, int C, int H, int W, void* ws,
+                   int64_t ws_bytes, cudaStream_t st);
 
 }  // namespace smow

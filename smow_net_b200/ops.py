@@ -148,6 +148,14 @@ def tlerp_bwd_bytes(B, Cs, hw, s):
     return B * 6 * Cs * hw * s
 
 
+def _bwd_workspace(lib, like, layout, B, H, W):
+    """Scratch for the deterministic NDHWC gather backward (caller-owned: the C ABI never allocates)."""
+    if layout != _lib.NDHWC or like.dtype != torch.float32:
+        return None, 0
+    n = int(lib.smow_warp_bwd_workspace_bytes(B, H, W))
+    return torch.empty(n, dtype=torch.uint8, device=like.device), n
+
+
 # ----------------------------------------------------------------------------- A1: warp + stack
 class _WarpStack(torch.autograd.Function):
     @staticmethod
@@ -180,10 +188,12 @@ class _WarpStack(torch.autograd.Function):
         gflow = torch.empty_like(flow)
         xs, ys = base_grid(W, x.device), base_grid(H, x.device)
         lib = _lib.load()
+        ws, ws_bytes = _bwd_workspace(lib, x, ctx.layout, B, H, W)
         with torch.cuda.device_of(x):
             _call("warp_stack_bwd", warp_bwd_bytes(B, C, H, W, x.element_size()), lib.smow_warp_stack_bwd,
                   gout.data_ptr(), x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),
-                  gx.data_ptr(), gflow.data_ptr(), B, C, H, W, _dtype_code(x), ctx.layout, _stream())
+                  gx.data_ptr(), gflow.data_ptr(), B, C, H, W, _dtype_code(x), ctx.layout,
+                  ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
         return gx, gflow
 
 
@@ -221,10 +231,11 @@ class _WarpPair(torch.autograd.Function):
         xs, ys = base_grid(W, x1.device), base_grid(H, x1.device)
         lib = _lib.load()
         with torch.cuda.device_of(x1):
+            ws, ws_bytes = _bwd_workspace(lib, x1, ctx.layout, B, H, W)
             _call("warp_stack_bwd", warp_bwd_bytes(B, C, H, W, x1.element_size()), lib.smow_warp_pair_bwd,
                   gout.data_ptr(), x1.data_ptr(), x2.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),
                   g1.data_ptr(), g2.data_ptr(), gflow.data_ptr(), B, C, H, W, _dtype_code(x1), ctx.layout,
-                  _stream())
+                  ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
         return g1, g2, gflow
 
 

@@ -47,7 +47,7 @@ def test_warp_kernels_stay_inside_their_buffers(shape, fv, bv):
         gb, gx = guarded(n_gx)
         fb, gf = guarded(n_gf)
         _lib.check(lib.smow_warp_stack_bwd(gout.data_ptr(), x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),
-                                           gx.data_ptr(), gf.data_ptr(), B, C, H, W, 0, 0, st), "bwd")
+                                           gx.data_ptr(), gf.data_ptr(), B, C, H, W, 0, 0, None, 0, st), "bwd")
         torch.cuda.synchronize()
         assert intact(ob, n_out) and intact(gb, n_gx) and intact(fb, n_gf)
         assert bool((out != MAGIC).all()) and bool((gx != MAGIC).all()) and bool((gf != MAGIC).all())   # fully written

@@ -299,6 +299,23 @@ def test_warp_ndhwc_against_same_device_reference(case):
     assert torch.equal(out[:, :, 0], x[:, :, 0]) and torch.equal(out[:, :, 3], x[:, :, 1])
 
 
+def test_warp_ndhwc_gather_backward_is_deterministic_and_matches_scatter(variants):
+    """With the caller's workspace the NDHWC backward is a fixed-order gather (bit-reproducible); forcing
+    warp_bwd_variant=0 selects the vector-atomic scatter, which must agree with it."""
+    g = torch.Generator(device=DEV).manual_seed(31)
+    x = torch.randn(3, 16, 2, 128, 128, device=DEV, generator=g).contiguous(memory_format=CL3)
+    flow = torch.randn(3, 2, 2, 128, 128, device=DEV, generator=g) * 0.6
+    gout = torch.randn(3, 16, 4, 128, 128, device=DEV, generator=g).contiguous(memory_format=CL3)
+    before = _lib.launch_count()
+    a = run_warp(x, flow, gout)
+    assert _lib.launch_count() - before == 1 + 5          # forward + (header, stat, gather, 2 early-exit scatter kernels)
+    b = run_warp(x, flow, gout)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    _lib.set_option("warp_bwd_variant", 0)
+    c = run_warp(x, flow, gout)
+    assert float((a[1] - c[1]).abs().max()) <= 1e-5 and float((a[2] - c[2]).abs().max()) <= 1e-5 * _scale(a[2])
+
+
 def test_warp_ndhwc_bf16_forward():
     g = torch.Generator(device=DEV).manual_seed(2)
     x = torch.randn(2, 32, 2, 64, 64, device=DEV, generator=g).bfloat16().contiguous(memory_format=CL3)
