@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--sigma", type=float, default=0.3)
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--layout", default="ncdhw", choices=["ncdhw", "ndhwc"])
     a = ap.parse_args()
     dt = torch.float32 if a.dtype == "f32" else torch.bfloat16
     dev = "cuda:0"
@@ -30,13 +31,17 @@ def main():
     flow = (torch.randn(a.B, 2, 2, a.H, a.H, device=dev, generator=g) * a.sigma).requires_grad_(True)
     gout = torch.randn(a.B, a.C, 4, a.H, a.H, device=dev, generator=g).to(dt)
     dec = torch.randn(a.B, a.C, 4, a.H, a.H, device=dev, generator=g).to(dt)
+    if a.layout == "ndhwc":
+        cl = torch.channels_last_3d
+        x = x.detach().contiguous(memory_format=cl).requires_grad_(True)
+        gout, dec = gout.contiguous(memory_format=cl), dec.contiguous(memory_format=cl)
     for i in range(a.iters):
         with ops.kernel_timer() as kt:
             out = ops.flow_warp(x, flow, (a.H, a.H))
             out.backward(gout)
             x.grad = flow.grad = None
             cat = ops.tlerp_cat(dec, x)
-            cat.backward(torch.cat([gout, gout], 1))
+            cat.backward(torch.cat([gout, gout], 1).contiguous(memory_format=torch.channels_last_3d if a.layout == 'ndhwc' else torch.contiguous_format))
             x.grad = None
             torch.cuda.synchronize()
         print(i, {k: "%.3f ms %.0f GB/s" % (v["ms"], v["gbps"]) for k, v in kt.summary().items()})

@@ -219,7 +219,7 @@ extern "C" {
 
 int64_t smow_warp_bwd_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return 64 + (int64_t)B * 2 * 2 * H * W * (int64_t)sizeof(float);   // header + (ix, iy) of every pixel-frame
+  return warp_bwd_ndhwc_workspace_bytes(B, H, W);   // header + coordinates, anchors and gather lists of every pixel-frame
 }
 
 int smow_warp_pair_fwd(const void* x_t1, const void* x_t2, const float* flow, const float* xs,

@@ -103,118 +103,53 @@ warp_fwd_ndhwc_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int64_
       __ldg(reinterpret_cast<const uint4*>(src + (int64_t)p * C));    // un-warped slot: bit-exact copy
 }
 
-// gx[b,t] = gout[b, pass(t)]  (+ zero the flow gradient when it is accumulated with atomics)
-template <typename T>
-__global__ void __launch_bounds__(256)
-warp_bwd_ndhwc_init_kernel(const T* __restrict__ gout, T* __restrict__ gx1, T* __restrict__ gx2, int64_t sB,
-                           float* __restrict__ gflow, int C, int HW, int q, bool zero_gflow, const int* __restrict__ hdr) {
-  constexpr int V = CVec<T>::N;
-  if (hdr != nullptr) {               // gather mode: only the (rare, wide-C) atomic flow-gradient needs zeroing
-    const int nx = hdr[1] - hdr[0] + 2, ny = hdr[3] - hdr[2] + 2;
-    if (nx > 0 && ny > 0 && nx * ny <= 49) {
-      const int i = blockIdx.x * 256 + threadIdx.x;
-      if (zero_gflow && i < HW) {
-        const int64_t fo = ((int64_t)((blockIdx.y >> 1) * 2) * 2 + (blockIdx.y & 1)) * HW + i;
-        gflow[fo] = 0.f; gflow[fo + 2 * (int64_t)HW] = 0.f;
-      }
-      return;
-    }
-  }
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx >= HW * q) return;
-  const int b = blockIdx.y >> 1, t = blockIdx.y & 1;
-  const int64_t e = (int64_t)idx * V;                        // element offset inside one (b, frame) plane
-  *reinterpret_cast<uint4*>((t ? gx2 : gx1) + b * sB + e) =
-      __ldg(reinterpret_cast<const uint4*>(gout + ((int64_t)(b * 4 + (t ? 3 : 0)) * HW) * C + e));
-  if (zero_gflow && idx < HW) {
-    const int64_t fo = ((int64_t)(b * 2) * 2 + t) * HW + idx;
-    gflow[fo] = 0.f; gflow[fo + 2 * (int64_t)HW] = 0.f;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-warp_bwd_ndhwc_scatter_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
-                              int64_t sB, const float* __restrict__ flow, const float* __restrict__ xs,
-                              const float* __restrict__ ys, float* __restrict__ gx1, float* __restrict__ gx2,
-                              float* __restrict__ gflow, int C, int H, int W, int q, int qshift, bool shuffle_reduce,
-                              const int* __restrict__ hdr) {
-  if (hdr != nullptr) {               // the gather kernel already produced this launch's gradients
-    const int nx = hdr[1] - hdr[0] + 2, ny = hdr[3] - hdr[2] + 2;
-    if (nx > 0 && ny > 0 && nx * ny <= 49) return;
-  }
-  const int HW = H * W;
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  const bool live = idx < HW * q;
-  int p = 0, v = 0;
-  if (live) split_item(idx, q, qshift, p, v);
-  const int b = blockIdx.y >> 1, t = blockIdx.y & 1;
-  float gix = 0.f, giy = 0.f, mx = 0.f, my = 0.f;
-  int64_t fo = 0;
-  if (live) {
-    const int h = p / W, w = p - h * W;
-    fo = ((int64_t)(b * 2) * 2 + t) * HW + p;
-    const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
-    const float nw = __fmul_rn(fp.wx0, fp.wy0), ne = __fmul_rn(fp.wx1, fp.wy0);
-    const float sw = __fmul_rn(fp.wx0, fp.wy1), se = __fmul_rn(fp.wx1, fp.wy1);
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gout + ((int64_t)(b * 4 + 1 + t) * HW + p) * C + v * 4));
-    const int o_nw = fp.y0 * W + fp.x0;
-    const float* src = (t ? x2 : x1) + b * sB + v * 4;
-    float* dst = (t ? gx2 : gx1) + b * sB + v * 4;
-    auto tap = [&](int off, float wgt, float dgx, float dgy) {
-      atomicAdd(reinterpret_cast<float4*>(dst + (int64_t)off * C), make_float4(wgt * g.x, wgt * g.y, wgt * g.z, wgt * g.w));
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(src + (int64_t)off * C));
-      const float dot = fmaf(xv.w, g.w, fmaf(xv.z, g.z, fmaf(xv.y, g.y, __fmul_rn(xv.x, g.x))));
-      gix = fmaf(dgx, dot, gix);
-      giy = fmaf(dgy, dot, giy);
-    };
-    tap(o_nw, nw, -fp.wy0, -fp.wx0);
-    if (fp.x1ok) tap(o_nw + 1, ne, fp.wy0, -fp.wx1);
-    if (fp.y1ok) tap(o_nw + W, sw, -fp.wy1, fp.wx0);
-    if (fp.x1ok && fp.y1ok) tap(o_nw + W + 1, se, fp.wy1, fp.wx1);
-    mx = __fmul_rn(fp.gx_gate, __fmul_rn((float)(W - 1), 0.5f));
-    my = __fmul_rn(fp.gy_gate, __fmul_rn((float)(H - 1), 0.5f));
-  }
-  if (shuffle_reduce) {      // q is a power of two: the lanes of a pixel are adjacent, butterfly over min(q, 32) of them
-    const int span = q < 32 ? q : 32;
-    for (int d = span >> 1; d > 0; d >>= 1) {
-      gix += __shfl_xor_sync(0xffffffffu, gix, d);
-      giy += __shfl_xor_sync(0xffffffffu, giy, d);
-    }
-    if (live && (v & (span - 1)) == 0) {
-      if (q <= 32) {
-        gflow[fo] = __fdiv_rn(__fmul_rn(mx, gix), (float)W);
-        gflow[fo + 2 * (int64_t)HW] = __fdiv_rn(__fmul_rn(my, giy), (float)H);
-      } else {               // several warps share a pixel: one atomic per warp into the zeroed gradient
-        atomicAdd(gflow + fo, __fdiv_rn(__fmul_rn(mx, gix), (float)W));
-        atomicAdd(gflow + fo + 2 * (int64_t)HW, __fdiv_rn(__fmul_rn(my, giy), (float)H));
-      }
-    }
-  } else if (live) {
-    atomicAdd(gflow + fo, __fdiv_rn(__fmul_rn(mx, gix), (float)W));
-    atomicAdd(gflow + fo + 2 * (int64_t)HW, __fdiv_rn(__fmul_rn(my, giy), (float)H));
-  }
-}
-
-
 // ------------------------------------------------------------------------------
-// deterministic gather backward (needs the caller's workspace)
+// backward
 // ------------------------------------------------------------------------------
-// workspace: [0..3] int header {dxmin, dxmax, dymin, dymax} = range of the integer displacement
-// (anchor - pixel) over the whole launch, then two float planes (ix, iy) of B*2*HW clipped sample coordinates.
-constexpr int GATHER_MAX_WINDOW = 49;     // candidates per target beyond which the atomic scatter takes over
+// Two strategies behind one entry point:
+//  (G) deterministic gather — needs the caller's workspace.  stat: clipped sample coordinates + packed anchors
+//      of every pixel, and the launch-wide range of integer displacements; list: ONE thread per pixel scans
+//      the few sources that can cover it and writes a (weight, source) list — per pixel, not per channel;
+//      apply: one thread per (pixel, 4-channel vector) reads the list (broadcast loads) and does
+//      gx = gout[pass] + sum w * gout[warp][src] with plain 16-byte stores, plus the flow-gradient sums.
+//      No float atomics, no zero-fill, fixed summation order => bit-reproducible.
+//  (S) vector-atomic scatter — any displacement: gx <- gout[pass], then one red.global.add.v4.f32 per tap.
+// The choice is made ON THE DEVICE (no host sync): stat/list publish the displacement window and a list
+// overflow flag in the workspace header; (G)'s apply kernel and (S)'s kernels each read it and exactly one of
+// the two families does the work, the other exits at once.
+constexpr int GATHER_MAX_WINDOW = 49;   // candidate sources per target beyond which (S) takes over
+constexpr int LIST_K = 8;               // list entries per target; more than that => (S)
 
-__device__ __forceinline__ bool gather_enabled(const int* hdr) {
+struct BwdWs {        // views into the caller's workspace
+  int* hdr;           // {dxmin, dxmax, dymin, dymax, overflow}
+  float* cix; float* ciy; int* can;     // per pixel-frame: clipped coordinates, packed anchor
+  int* cnt; float* lw; int* ls;         // per pixel-frame: list length; [LIST_K][N] weights and source pixels
+};
+__host__ __device__ inline int64_t bwd_ws_bytes(int64_t n) { return 64 + n * (3 + 1 + 2 * LIST_K) * 4; }
+static BwdWs carve_ws(void* ws, int64_t n) {
+  BwdWs w;
+  w.hdr = reinterpret_cast<int*>(ws);
+  w.cix = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 64);
+  w.ciy = w.cix + n;
+  w.can = reinterpret_cast<int*>(w.ciy + n);
+  w.cnt = w.can + n;
+  w.lw = reinterpret_cast<float*>(w.cnt + n);
+  w.ls = reinterpret_cast<int*>(w.lw + LIST_K * n);
+  return w;
+}
+__device__ __forceinline__ bool gather_active(const int* hdr) {
   const int nx = hdr[1] - hdr[0] + 2, ny = hdr[3] - hdr[2] + 2;
-  return nx > 0 && ny > 0 && nx * ny <= GATHER_MAX_WINDOW;
+  return nx > 0 && ny > 0 && nx * ny <= GATHER_MAX_WINDOW && hdr[4] == 0;
 }
 
 __global__ void warp_bwd_ndhwc_hdr_kernel(int* hdr) {
   if (threadIdx.x < 4) hdr[threadIdx.x] = (threadIdx.x & 1) ? -(1 << 30) : (1 << 30);
+  if (threadIdx.x == 4) hdr[4] = 0;
 }
 
 __global__ void __launch_bounds__(256)
 warp_bwd_ndhwc_stat_kernel(const float* __restrict__ flow, const float* __restrict__ xs, const float* __restrict__ ys,
-                           int* __restrict__ hdr, float* __restrict__ cix, float* __restrict__ ciy, int H, int W) {
+                           BwdWs ws, int H, int W) {
   __shared__ int red[4];
   const int HW = H * W;
   const int p = blockIdx.x * 256 + threadIdx.x;
@@ -227,8 +162,9 @@ warp_bwd_ndhwc_stat_kernel(const float* __restrict__ flow, const float* __restri
     const int64_t fo = ((int64_t)(b * 2) * 2 + t) * HW + p;
     const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
     const int64_t o = (int64_t)(b * 2 + t) * HW + p;
-    cix[o] = __fadd_rn((float)fp.x0, fp.wx1);          // = ix exactly (wx1 = ix - floor(ix))
-    ciy[o] = __fadd_rn((float)fp.y0, fp.wy1);
+    ws.cix[o] = __fadd_rn((float)fp.x0, fp.wx1);          // = ix exactly (wx1 = ix - floor(ix))
+    ws.ciy[o] = __fadd_rn((float)fp.y0, fp.wy1);
+    ws.can[o] = (fp.y0 << 16) | fp.x0;
     dx0 = dx1 = fp.x0 - w; dy0 = dy1 = fp.y0 - h;
   }
   dx0 = __reduce_min_sync(0xffffffffu, dx0); dx1 = __reduce_max_sync(0xffffffffu, dx1);
@@ -237,22 +173,60 @@ warp_bwd_ndhwc_stat_kernel(const float* __restrict__ flow, const float* __restri
     atomicMin(red + 0, dx0); atomicMax(red + 1, dx1); atomicMin(red + 2, dy0); atomicMax(red + 3, dy1);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    atomicMin(hdr + 0, red[0]); atomicMax(hdr + 1, red[1]); atomicMin(hdr + 2, red[2]); atomicMax(hdr + 3, red[3]);
+  if (threadIdx.x == 0) {   // same-address L2 atomics serialise: only blocks that widen the range issue one
+    if (red[0] < *(volatile int*)(ws.hdr + 0)) atomicMin(ws.hdr + 0, red[0]);
+    if (red[1] > *(volatile int*)(ws.hdr + 1)) atomicMax(ws.hdr + 1, red[1]);
+    if (red[2] < *(volatile int*)(ws.hdr + 2)) atomicMin(ws.hdr + 2, red[2]);
+    if (red[3] > *(volatile int*)(ws.hdr + 3)) atomicMax(ws.hdr + 3, red[3]);
   }
 }
 
-// thread = (pixel, 4-channel vector).  Target side: gx = gout[pass] + sum over the sources whose bilinear
-// footprint covers this pixel (found by scanning the coordinate planes in a fixed order: bit-reproducible);
-// source side: flow-gradient sums of this pixel's own footprint, combined over the lanes of the pixel.
+// one thread per target pixel-frame: scan the candidate window in fixed (row-major) order
 __global__ void __launch_bounds__(256)
-warp_bwd_ndhwc_gather_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
-                             int64_t sB, const float* __restrict__ flow, const float* __restrict__ xs,
-                             const float* __restrict__ ys, const int* __restrict__ hdr, const float* __restrict__ cix,
-                             const float* __restrict__ ciy, float* __restrict__ gx1, float* __restrict__ gx2,
-                             float* __restrict__ gflow, int C, int H, int W, int q, int qshift) {
-  if (!gather_enabled(hdr)) return;                       // the atomic scatter kernels handle this launch
-  const int dxlo = hdr[0], dxhi = hdr[1], dylo = hdr[2], dyhi = hdr[3];
+warp_bwd_ndhwc_list_kernel(BwdWs ws, int H, int W, int64_t n_pf) {
+  const int nx = ws.hdr[1] - ws.hdr[0] + 2, ny = ws.hdr[3] - ws.hdr[2] + 2;
+  if (!(nx > 0 && ny > 0 && nx * ny <= GATHER_MAX_WINDOW)) return;
+  const int dxlo = ws.hdr[0], dxhi = ws.hdr[1], dylo = ws.hdr[2], dyhi = ws.hdr[3];
+  const int HW = H * W;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= HW) return;
+  const int64_t plane = (int64_t)blockIdx.y * HW;          // blockIdx.y = b*2 + t
+  const int h = p / W, w = p - h * W;
+  const int* pa = ws.can + plane;
+  const float* px = ws.cix + plane;
+  const float* py = ws.ciy + plane;
+  const int sy_a = max(0, h - 1 - dyhi), sy_b = min(H - 1, h - dylo);
+  const int sx_a = max(0, w - 1 - dxhi), sx_b = min(W - 1, w - dxlo);
+  int n = 0;
+  for (int sy = sy_a; sy <= sy_b; ++sy) {
+    const int row = sy * W;
+    for (int sx = sx_a; sx <= sx_b; ++sx) {
+      const int an = __ldg(pa + row + sx);
+      const int x0 = an & 0xffff, y0 = an >> 16;
+      const unsigned ex = (unsigned)(w - x0), ey = (unsigned)(h - y0);
+      if ((ex | ey) > 1u) continue;
+      const float ix = __ldg(px + row + sx), iy = __ldg(py + row + sx);
+      const float x0f = (float)x0, y0f = (float)y0;
+      const float wx = ex ? __fsub_rn(ix, x0f) : __fsub_rn(__fadd_rn(x0f, 1.f), ix);
+      const float wy = ey ? __fsub_rn(iy, y0f) : __fsub_rn(__fadd_rn(y0f, 1.f), iy);
+      if (n < LIST_K) {
+        ws.lw[(int64_t)n * n_pf + plane + p] = __fmul_rn(wx, wy);
+        ws.ls[(int64_t)n * n_pf + plane + p] = row + sx;
+      }
+      ++n;
+    }
+  }
+  ws.cnt[plane + p] = n;
+  if (n > LIST_K) ws.hdr[4] = 1;          // benign race: every writer stores 1
+}
+
+// one thread per (pixel, 4-channel vector)
+__global__ void __launch_bounds__(256)
+warp_bwd_ndhwc_apply_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
+                            int64_t sB, const float* __restrict__ flow, const float* __restrict__ xs,
+                            const float* __restrict__ ys, BwdWs ws, float* __restrict__ gx1, float* __restrict__ gx2,
+                            float* __restrict__ gflow, int C, int H, int W, int q, int qshift, int64_t n_pf) {
+  if (!gather_active(ws.hdr)) return;
   const int HW = H * W;
   const int idx = blockIdx.x * 256 + threadIdx.x;
   const bool live = idx < HW * q;
@@ -264,33 +238,22 @@ warp_bwd_ndhwc_gather_kernel(const float* __restrict__ gout, const float* __rest
   if (live) {
     const int h = p / W, w = p - h * W;
     fo = ((int64_t)(b * 2) * 2 + t) * HW + p;
+    const int64_t pf = (int64_t)blockIdx.y * HW + p;
     const float* gw = gout + ((int64_t)(b * 4 + 1 + t) * HW) * C + v * 4;      // warped-slot gradient plane
-    // ---- target side ----
-    float4 acc = __ldg(reinterpret_cast<const float4*>(gout + ((int64_t)(b * 4 + (t ? 3 : 0)) * HW + p) * C + v * 4));
-    const float* px = cix + (int64_t)(b * 2 + t) * HW;
-    const float* py = ciy + (int64_t)(b * 2 + t) * HW;
-    const int sy_a = max(0, h - 1 - dyhi), sy_b = min(H - 1, h - dylo);
-    const int sx_a = max(0, w - 1 - dxhi), sx_b = min(W - 1, w - dxlo);
+    // ---- target side: pass-through + gathered scatter ----
+    const float4 pass = __ldg(reinterpret_cast<const float4*>(gout + ((int64_t)(b * 4 + (t ? 3 : 0)) * HW + p) * C + v * 4));
+    const int n = __ldg(ws.cnt + pf);
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int sy = sy_a; sy <= sy_b; ++sy) {
-      for (int sx = sx_a; sx <= sx_b; ++sx) {
-        const int s = sy * W + sx;
-        const float ix = __ldg(px + s), iy = __ldg(py + s);
-        const float x0f = floorf(ix), y0f = floorf(iy);
-        const unsigned ex = (unsigned)(w - (int)x0f), ey = (unsigned)(h - (int)y0f);
-        if ((ex | ey) > 1u) continue;
-        const float wx = ex ? __fsub_rn(ix, x0f) : __fsub_rn(__fadd_rn(x0f, 1.f), ix);
-        const float wy = ey ? __fsub_rn(iy, y0f) : __fsub_rn(__fadd_rn(y0f, 1.f), iy);
-        const float wgt = __fmul_rn(wx, wy);
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gw + (int64_t)s * C));
-        sum.x = fmaf(wgt, g.x, sum.x); sum.y = fmaf(wgt, g.y, sum.y);
-        sum.z = fmaf(wgt, g.z, sum.z); sum.w = fmaf(wgt, g.w, sum.w);
-      }
+    for (int j = 0; j < n; ++j) {
+      const float wgt = __ldg(ws.lw + (int64_t)j * n_pf + pf);
+      const int s = __ldg(ws.ls + (int64_t)j * n_pf + pf);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gw + (int64_t)s * C));
+      sum.x = fmaf(wgt, g.x, sum.x); sum.y = fmaf(wgt, g.y, sum.y);
+      sum.z = fmaf(wgt, g.z, sum.z); sum.w = fmaf(wgt, g.w, sum.w);
     }
-    acc.x = __fadd_rn(acc.x, sum.x); acc.y = __fadd_rn(acc.y, sum.y);
-    acc.z = __fadd_rn(acc.z, sum.z); acc.w = __fadd_rn(acc.w, sum.w);
-    *reinterpret_cast<float4*>((t ? gx2 : gx1) + b * sB + (int64_t)p * C + v * 4) = acc;
-    // ---- source side ----
+    *reinterpret_cast<float4*>((t ? gx2 : gx1) + b * sB + (int64_t)p * C + v * 4) =
+        make_float4(__fadd_rn(pass.x, sum.x), __fadd_rn(pass.y, sum.y), __fadd_rn(pass.z, sum.z), __fadd_rn(pass.w, sum.w));
+    // ---- source side: flow-gradient sums of this pixel's own footprint ----
     const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
     const float4 g = __ldg(reinterpret_cast<const float4*>(gw + (int64_t)p * C));
     const int o_nw = fp.y0 * W + fp.x0;
@@ -308,16 +271,103 @@ warp_bwd_ndhwc_gather_kernel(const float* __restrict__ gout, const float* __rest
     mx = __fmul_rn(fp.gx_gate, __fmul_rn((float)(W - 1), 0.5f));
     my = __fmul_rn(fp.gy_gate, __fmul_rn((float)(H - 1), 0.5f));
   }
-  const int span = q < 32 ? q : 32;       // q is a power of two here (checked by the host)
-  for (int d = span >> 1; d > 0; d >>= 1) {
+  for (int d = q >> 1; d > 0; d >>= 1) {      // q <= 32 and a power of two (host-checked): lanes of a pixel are adjacent
     gix += __shfl_xor_sync(0xffffffffu, gix, d);
     giy += __shfl_xor_sync(0xffffffffu, giy, d);
   }
-  if (live && (v & (span - 1)) == 0) {
-    if (q <= 32) {
-      gflow[fo] = __fdiv_rn(__fmul_rn(mx, gix), (float)W);
-      gflow[fo + 2 * (int64_t)HW] = __fdiv_rn(__fmul_rn(my, giy), (float)H);
-    } else {
+  if (live && v == 0) {
+    gflow[fo] = __fdiv_rn(__fmul_rn(mx, gix), (float)W);
+    gflow[fo + 2 * (int64_t)HW] = __fdiv_rn(__fmul_rn(my, giy), (float)H);
+  }
+}
+
+// ---- (S) vector-atomic scatter; both kernels are grid-stride over (plane, item) so that the "other family did
+// the work" exit costs a few hundred blocks, not one block per 256 items ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+warp_bwd_ndhwc_init_kernel(const T* __restrict__ gout, T* __restrict__ gx1, T* __restrict__ gx2, int64_t sB,
+                           float* __restrict__ gflow, int C, int HW, int q, int planes, bool zero_gflow,
+                           const int* __restrict__ hdr) {
+  constexpr int V = CVec<T>::N;
+  if (hdr != nullptr && gather_active(hdr)) return;
+  const int64_t per_plane = (int64_t)HW * q, total = per_plane * planes;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int bt = (int)(i / per_plane);
+    const int idx = (int)(i - (int64_t)bt * per_plane);
+    const int b = bt >> 1, t = bt & 1;
+    const int64_t e = (int64_t)idx * V;                        // element offset inside one (b, frame) plane
+    *reinterpret_cast<uint4*>((t ? gx2 : gx1) + b * sB + e) =
+        __ldg(reinterpret_cast<const uint4*>(gout + ((int64_t)(b * 4 + (t ? 3 : 0)) * HW) * C + e));
+    if (zero_gflow && idx < HW) {
+      const int64_t fo = ((int64_t)(b * 2) * 2 + t) * HW + idx;
+      gflow[fo] = 0.f; gflow[fo + 2 * (int64_t)HW] = 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+warp_bwd_ndhwc_scatter_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
+                              int64_t sB, const float* __restrict__ flow, const float* __restrict__ xs,
+                              const float* __restrict__ ys, float* __restrict__ gx1, float* __restrict__ gx2,
+                              float* __restrict__ gflow, int C, int H, int W, int q, int qshift, int planes,
+                              bool shuffle_reduce, const int* __restrict__ hdr) {
+  if (hdr != nullptr && gather_active(hdr)) return;
+  const int HW = H * W;
+  const int64_t per_plane = (int64_t)HW * q, total = per_plane * planes;
+  // every lane of a warp runs the same number of iterations (total is padded to the stride by the `live` flag)
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  const int64_t rounds = (total + stride - 1) / stride;
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (int64_t r = 0; r < rounds; ++r, i += stride) {
+    const bool live = i < total;
+    int p = 0, v = 0, b = 0, t = 0;
+    if (live) {
+      const int bt = (int)(i / per_plane);
+      split_item((int)(i - (int64_t)bt * per_plane), q, qshift, p, v);
+      b = bt >> 1; t = bt & 1;
+    }
+    float gix = 0.f, giy = 0.f, mx = 0.f, my = 0.f;
+    int64_t fo = 0;
+    if (live) {
+      const int h = p / W, w = p - h * W;
+      fo = ((int64_t)(b * 2) * 2 + t) * HW + p;
+      const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
+      const float nw = __fmul_rn(fp.wx0, fp.wy0), ne = __fmul_rn(fp.wx1, fp.wy0);
+      const float sw = __fmul_rn(fp.wx0, fp.wy1), se = __fmul_rn(fp.wx1, fp.wy1);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gout + ((int64_t)(b * 4 + 1 + t) * HW + p) * C + v * 4));
+      const int o_nw = fp.y0 * W + fp.x0;
+      const float* src = (t ? x2 : x1) + b * sB + v * 4;
+      float* dst = (t ? gx2 : gx1) + b * sB + v * 4;
+      auto tap = [&](int off, float wgt, float dgx, float dgy) {
+        atomicAdd(reinterpret_cast<float4*>(dst + (int64_t)off * C), make_float4(wgt * g.x, wgt * g.y, wgt * g.z, wgt * g.w));
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(src + (int64_t)off * C));
+        const float dot = fmaf(xv.w, g.w, fmaf(xv.z, g.z, fmaf(xv.y, g.y, __fmul_rn(xv.x, g.x))));
+        gix = fmaf(dgx, dot, gix);
+        giy = fmaf(dgy, dot, giy);
+      };
+      tap(o_nw, nw, -fp.wy0, -fp.wx0);
+      if (fp.x1ok) tap(o_nw + 1, ne, fp.wy0, -fp.wx1);
+      if (fp.y1ok) tap(o_nw + W, sw, -fp.wy1, fp.wx0);
+      if (fp.x1ok && fp.y1ok) tap(o_nw + W + 1, se, fp.wy1, fp.wx1);
+      mx = __fmul_rn(fp.gx_gate, __fmul_rn((float)(W - 1), 0.5f));
+      my = __fmul_rn(fp.gy_gate, __fmul_rn((float)(H - 1), 0.5f));
+    }
+    if (shuffle_reduce) {      // q is a power of two: the lanes of a pixel are adjacent, butterfly over min(q, 32) of them
+      const int span = q < 32 ? q : 32;
+      for (int d = span >> 1; d > 0; d >>= 1) {
+        gix += __shfl_xor_sync(0xffffffffu, gix, d);
+        giy += __shfl_xor_sync(0xffffffffu, giy, d);
+      }
+      if (live && (v & (span - 1)) == 0) {
+        if (q <= 32) {
+          gflow[fo] = __fdiv_rn(__fmul_rn(mx, gix), (float)W);
+          gflow[fo + 2 * (int64_t)HW] = __fdiv_rn(__fmul_rn(my, giy), (float)H);
+        } else {               // several warps share a pixel: one atomic per warp into the zeroed gradient
+          atomicAdd(gflow + fo, __fdiv_rn(__fmul_rn(mx, gix), (float)W));
+          atomicAdd(gflow + fo + 2 * (int64_t)HW, __fdiv_rn(__fmul_rn(my, giy), (float)H));
+        }
+      }
+    } else if (live) {
       atomicAdd(gflow + fo, __fdiv_rn(__fmul_rn(mx, gix), (float)W));
       atomicAdd(gflow + fo + 2 * (int64_t)HW, __fdiv_rn(__fmul_rn(my, giy), (float)H));
     }
@@ -329,6 +379,8 @@ static int ilog2_exact(int q) {
     if ((1 << s) == q) return s;
   return -1;
 }
+
+int64_t warp_bwd_ndhwc_workspace_bytes(int B, int H, int W) { return bwd_ws_bytes((int64_t)B * 2 * H * W); }
 
 template <typename T>
 int warp_fwd_ndhwc(const T* x1, const T* x2, int64_t sB, const float* flow, const float* xs, const float* ys, T* out,
@@ -354,27 +406,33 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
     if (C % 4 || !aligned16(gout) || !aligned16(x1) || !aligned16(x2) || !aligned16(gx1) || !aligned16(gx2) || sB % 4)
       return fail(SMOW_EALIGN, "NDHWC warp needs C %% 4 == 0 and 16 B aligned tensors");
     const int q = C / 4, qs = ilog2_exact(q);
-    if ((int64_t)H * W * q >= (1ll << 31)) return fail(SMOW_ERANGE, "plane too large");
-    const bool shuffle = qs >= 0;
     const int HW = H * W;
+    if ((int64_t)HW * q >= (1ll << 31)) return fail(SMOW_ERANGE, "plane too large");
+    const bool shuffle = qs >= 0;
+    const int64_t n_pf = (int64_t)B * 2 * HW;
     dim3 grid((unsigned)(((int64_t)HW * q + 255) / 256), 2 * B);
-    // deterministic gather when the caller lent a workspace (and the lanes of a pixel can be shuffle-reduced)
-    const int64_t need = 64 + (int64_t)B * 2 * 2 * HW * (int64_t)sizeof(float);
     int* hdr = nullptr;
     int launches = 2;
-    if (ws != nullptr && ws_bytes >= need && shuffle && q <= 32 && aligned16(ws) && option(OPT_WARP_BWD_VARIANT) != 0) {
-      hdr = reinterpret_cast<int*>(ws);
-      float* cix = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 64);
-      float* ciy = cix + (int64_t)B * 2 * HW;
-      warp_bwd_ndhwc_hdr_kernel<<<1, 32, 0, st>>>(hdr);   // min/max sentinels
-      warp_bwd_ndhwc_stat_kernel<<<dim3((HW + 255) / 256, 2 * B), 256, 0, st>>>(flow, xs, ys, hdr, cix, ciy, H, W);
-      warp_bwd_ndhwc_gather_kernel<<<grid, 256, 0, st>>>(gout, x1, x2, sB, flow, xs, ys, hdr, cix, ciy, gx1, gx2, gflow,
-                                                         C, H, W, q, qs);
-      launches += 3;
+    // (G) when the caller lent a workspace and the lanes of a pixel fit one warp; knob 0 forces (S)
+    if (ws != nullptr && ws_bytes >= bwd_ws_bytes(n_pf) && shuffle && q <= 32 && aligned16(ws) &&
+        option(OPT_WARP_BWD_VARIANT) != 0) {
+      const BwdWs w = carve_ws(ws, n_pf);
+      hdr = w.hdr;
+      dim3 pgrid((HW + 255) / 256, 2 * B);
+      warp_bwd_ndhwc_hdr_kernel<<<1, 32, 0, st>>>(hdr);
+      warp_bwd_ndhwc_stat_kernel<<<pgrid, 256, 0, st>>>(flow, xs, ys, w, H, W);
+      warp_bwd_ndhwc_list_kernel<<<pgrid, 256, 0, st>>>(w, H, W, n_pf);
+      warp_bwd_ndhwc_apply_kernel<<<grid, 256, 0, st>>>(gout, x1, x2, sB, flow, xs, ys, w, gx1, gx2, gflow, C, H, W, q, qs,
+                                                        n_pf);
+      launches += 4;
     }
-    warp_bwd_ndhwc_init_kernel<float><<<grid, 256, 0, st>>>(gout, gx1, gx2, sB, gflow, C, HW, q, !shuffle || q > 32, hdr);
-    warp_bwd_ndhwc_scatter_kernel<<<grid, 256, 0, st>>>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, C, H, W, q, qs,
-                                                        shuffle, hdr);
+    const int64_t items = (int64_t)HW * q * 2 * B;
+    const int cap = device_info().sms * 16;
+    const int sgrid = (int)((items + 255) / 256 < cap ? (items + 255) / 256 : cap);
+    warp_bwd_ndhwc_init_kernel<float><<<sgrid, 256, 0, st>>>(gout, gx1, gx2, sB, gflow, C, HW, q, 2 * B,
+                                                             !shuffle || q > 32, hdr);
+    warp_bwd_ndhwc_scatter_kernel<<<sgrid, 256, 0, st>>>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, C, H, W, q, qs,
+                                                         2 * B, shuffle, hdr);
     count_launch(launches);
     return check_launch("warp_bwd_ndhwc");
   }

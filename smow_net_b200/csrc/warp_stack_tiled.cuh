@@ -225,6 +225,7 @@ int warp_fwd_cvec(const float* x1, const float* x2, int64_t sB, int64_t sC, cons
 int warp_bwd_cvec(const float* gout, const float* x1, const float* x2, int64_t sB, int64_t sC, const float* flow,
                   const float* xs, const float* ys, float* gx1, float* gx2, float* gflow, int B, int C, int H,
                   int W, cudaStream_t st);
+int64_t warp_bwd_ndhwc_workspace_bytes(int B, int H, int W);
 template <typename T>
 int warp_fwd_ndhwc(const T* x1, const T* x2, int64_t sB, const float* flow, const float* xs, const float* ys,
                    T* out, int B, int C, int H, int W, cudaStream_t st);

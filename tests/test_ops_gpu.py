@@ -308,7 +308,7 @@ def test_warp_ndhwc_gather_backward_is_deterministic_and_matches_scatter(variant
     gout = torch.randn(3, 16, 4, 128, 128, device=DEV, generator=g).contiguous(memory_format=CL3)
     before = _lib.launch_count()
     a = run_warp(x, flow, gout)
-    assert _lib.launch_count() - before == 1 + 5          # forward + (header, stat, gather, 2 early-exit scatter kernels)
+    assert _lib.launch_count() - before == 1 + 6          # forward + (header, stat, list, apply, 2 early-exit scatter kernels)
     b = run_warp(x, flow, gout)
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     _lib.set_option("warp_bwd_variant", 0)
