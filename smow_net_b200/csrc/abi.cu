@@ -12,7 +12,7 @@ static std::atomic<uint64_t> g_launches{0};
 struct Knob { const char* key; std::atomic<int> value; };
 static Knob g_knobs[OPT_COUNT] = {
     {"warp_fwd_variant", {-1}},  // -1 = auto, 0 = direct L1 gather, 1 = bulk-copy staged planes, 2 = channel-vectorised tiles
-    {"warp_bwd_variant", {-1}},  // -1 = auto, 0 = global-atomic scatter, 1 = tiled inverse-gather, 2 = channel-vectorised
+    {"warp_bwd_variant", {-1}},  // -1 = auto, 0 = atomic scatter, 1 = tiled gather, 2 = channel-vectorised gather, 3 = deterministic (NDHWC gather lists)
     {"tlerp_variant", {0}},
     {"bwd_rows", {8}},
     {"bwd_halo", {2}},

@@ -187,8 +187,9 @@ static int bwd_impl(const T* gout, const T* x1, const T* x2, int64_t sB, int64_t
   if (layout == SMOW_NDHWC)
     return warp_bwd_ndhwc<T>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, B, C, H, W, ws, ws_bytes, st);
   int variant = option(OPT_WARP_BWD_VARIANT);
-  if (variant < -1 || variant > 2) return fail(SMOW_EINVAL, "unknown warp_bwd_variant %d", variant);
-  if (variant == -1) variant = 2;   // falls through to 1 for bf16 / uncovered shapes, then to 0
+  if (variant < -1 || variant > 3) return fail(SMOW_EINVAL, "unknown warp_bwd_variant %d", variant);
+  if (variant == -1 || variant == 3) variant = 2;   // NCDHW: the tile gathers are deterministic already; falls
+                                                     // through to 1 for bf16 / uncovered shapes, then to 0
   const bool tile_ok = tiled_shape_ok<T>(x1, x2, gout, sB, sC, C, H, W) && aligned16(gx1) && aligned16(gx2);
   if constexpr (std::is_same<T, float>::value) {
     if (variant == 2 && tile_ok) {

@@ -118,7 +118,7 @@ warp_fwd_ndhwc_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int64_
 // overflow flag in the workspace header; (G)'s apply kernel and (S)'s kernels each read it and exactly one of
 // the two families does the work, the other exits at once.
 constexpr int GATHER_MAX_WINDOW = 49;   // candidate sources per target beyond which (S) takes over
-constexpr int LIST_K = 8;               // list entries per target; more than that => (S)
+constexpr int LIST_K = 9;               // list entries per target (a 3x3 window can never overflow it); more => (S)
 
 struct BwdWs {        // views into the caller's workspace
   int* hdr;           // {dxmin, dxmax, dymin, dymax, overflow}
@@ -412,10 +412,12 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
     const int64_t n_pf = (int64_t)B * 2 * HW;
     dim3 grid((unsigned)(((int64_t)HW * q + 255) / 256), 2 * B);
     int* hdr = nullptr;
-    int launches = 2;
-    // (G) when the caller lent a workspace and the lanes of a pixel fit one warp; knob 0 forces (S)
-    if (ws != nullptr && ws_bytes >= bwd_ws_bytes(n_pf) && shuffle && q <= 32 && aligned16(ws) &&
-        option(OPT_WARP_BWD_VARIANT) != 0) {
+    int launches = 0;
+    // (G) only on request (warp_bwd_variant = 3: bit-reproducible gradients) and with a workspace: on B200 the
+    // vector-atomic scatter is the faster of the two (profiles/r1_notes.md)
+    const bool gather = option(OPT_WARP_BWD_VARIANT) == 3 && ws != nullptr && ws_bytes >= bwd_ws_bytes(n_pf) &&
+                        shuffle && q <= 32 && aligned16(ws);
+    if (gather) {
       const BwdWs w = carve_ws(ws, n_pf);
       hdr = w.hdr;
       dim3 pgrid((HW + 255) / 256, 2 * B);
@@ -426,13 +428,25 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
                                                         n_pf);
       launches += 4;
     }
-    const int64_t items = (int64_t)HW * q * 2 * B;
+    // (S) in batch chunks sized for the L2: a chunk's gx lines are still L2-resident when its vector reductions
+    // arrive, so the read-modify-write never reaches HBM (one chunk for the models' per-GPU batches)
+    const int64_t per_pair = (int64_t)16 * C * HW * (int64_t)sizeof(float);     // pass + gx + warp-slot + x, both frames
+    int bc = (int)((int64_t)96 * 1024 * 1024 / per_pair);
+    if (bc < 1) bc = 1;
     const int cap = device_info().sms * 16;
-    const int sgrid = (int)((items + 255) / 256 < cap ? (items + 255) / 256 : cap);
-    warp_bwd_ndhwc_init_kernel<float><<<sgrid, 256, 0, st>>>(gout, gx1, gx2, sB, gflow, C, HW, q, 2 * B,
-                                                             !shuffle || q > 32, hdr);
-    warp_bwd_ndhwc_scatter_kernel<<<sgrid, 256, 0, st>>>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, C, H, W, q, qs,
-                                                         2 * B, shuffle, hdr);
+    for (int b0 = 0; b0 < B; b0 += bc) {
+      const int nb = (B - b0) < bc ? (B - b0) : bc;
+      const int64_t items = (int64_t)HW * q * 2 * nb;
+      const int sgrid = (int)((items + 255) / 256 < cap ? (items + 255) / 256 : cap);
+      const float* g0 = gout + (int64_t)b0 * 4 * HW * C;
+      const float* f0 = flow + (int64_t)b0 * 4 * HW;
+      float* gf0 = gflow + (int64_t)b0 * 4 * HW;
+      warp_bwd_ndhwc_init_kernel<float><<<sgrid, 256, 0, st>>>(g0, gx1 + b0 * sB, gx2 + b0 * sB, sB, gf0, C, HW, q, 2 * nb,
+                                                               !shuffle || q > 32, hdr);
+      warp_bwd_ndhwc_scatter_kernel<<<sgrid, 256, 0, st>>>(g0, x1 + b0 * sB, x2 + b0 * sB, sB, f0, xs, ys, gx1 + b0 * sB,
+                                                           gx2 + b0 * sB, gf0, C, H, W, q, qs, 2 * nb, shuffle, hdr);
+      launches += 2;
+    }
     count_launch(launches);
     return check_launch("warp_bwd_ndhwc");
   }

@@ -150,7 +150,7 @@ def tlerp_bwd_bytes(B, Cs, hw, s):
 
 def _bwd_workspace(lib, like, layout, B, H, W):
     """Scratch for the deterministic NDHWC gather backward (caller-owned: the C ABI never allocates)."""
-    if layout != _lib.NDHWC or like.dtype != torch.float32:
+    if layout != _lib.NDHWC or like.dtype != torch.float32 or _lib.get_option("warp_bwd_variant") != 3:
         return None, 0
     n = int(lib.smow_warp_bwd_workspace_bytes(B, H, W))
     return torch.empty(n, dtype=torch.uint8, device=like.device), n

@@ -300,8 +300,9 @@ def test_warp_ndhwc_against_same_device_reference(case):
 
 
 def test_warp_ndhwc_gather_backward_is_deterministic_and_matches_scatter(variants):
-    """With the caller's workspace the NDHWC backward is a fixed-order gather (bit-reproducible); forcing
-    warp_bwd_variant=0 selects the vector-atomic scatter, which must agree with it."""
+    """warp_bwd_variant=3 + the caller's workspace: the NDHWC backward is a fixed-order gather (bit-reproducible);
+    the default vector-atomic scatter must agree with it."""
+    _lib.set_option("warp_bwd_variant", 3)
     g = torch.Generator(device=DEV).manual_seed(31)
     x = torch.randn(3, 16, 2, 128, 128, device=DEV, generator=g).contiguous(memory_format=CL3)
     flow = torch.randn(3, 2, 2, 128, 128, device=DEV, generator=g) * 0.6
@@ -311,8 +312,10 @@ def test_warp_ndhwc_gather_backward_is_deterministic_and_matches_scatter(variant
     assert _lib.launch_count() - before == 1 + 6          # forward + (header, stat, list, apply, 2 early-exit scatter kernels)
     b = run_warp(x, flow, gout)
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
-    _lib.set_option("warp_bwd_variant", 0)
+    _lib.set_option("warp_bwd_variant", -1)
+    before = _lib.launch_count()
     c = run_warp(x, flow, gout)
+    assert _lib.launch_count() - before == 1 + 2          # forward + (init, scatter) for one L2-sized chunk
     assert float((a[1] - c[1]).abs().max()) <= 1e-5 and float((a[2] - c[2]).abs().max()) <= 1e-5 * _scale(a[2])
 
 
