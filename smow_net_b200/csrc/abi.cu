@@ -19,6 +19,7 @@ static Knob g_knobs[OPT_COUNT] = {
     {"fwd_rows", {8}},
     {"fwd_halo", {2}},
     {"cvec_prefetch", {3}},      // L2 bulk-prefetch distance of the channel-vectorised kernels, in chunks (0 = off)
+    {"bwd_chunk_mb", {0}},       // NDHWC scatter: process the batch in chunks of about this many MB (0 = whole batch)
 };
 
 int fail(int code, const char* fmt, ...) {

@@ -430,10 +430,12 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
     }
     // (S) in batch chunks sized for the L2: a chunk's gx lines are still L2-resident when its vector reductions
     // arrive, so the read-modify-write never reaches HBM (one chunk for the models' per-GPU batches)
-    const int64_t per_pair = (int64_t)16 * C * HW * (int64_t)sizeof(float);     // pass + gx + warp-slot + x, both frames
-    int bc = (int)((int64_t)96 * 1024 * 1024 / per_pair);
+    // (knob bwd_chunk_mb, 0 = one chunk: measured on B200 the launch granularity costs more than the RMW saves)
+    const int64_t per_pair = (int64_t)10 * C * HW * (int64_t)sizeof(float);     // pass + gx + warp-slot + x, both frames
+    const int chunk_mb = option(OPT_BWD_CHUNK_MB);
+    int bc = chunk_mb > 0 ? (int)((int64_t)chunk_mb * 1024 * 1024 / per_pair) : B;
     if (bc < 1) bc = 1;
-    const int cap = device_info().sms * 16;
+    const int cap = device_info().sms * 64;
     for (int b0 = 0; b0 < B; b0 += bc) {
       const int nb = (B - b0) < bc ? (B - b0) : bc;
       const int64_t items = (int64_t)HW * q * 2 * nb;
