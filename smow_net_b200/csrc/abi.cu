@@ -12,7 +12,7 @@ static std::atomic<uint64_t> g_launches{0};
 struct Knob { const char* key; std::atomic<int> value; };
 static Knob g_knobs[OPT_COUNT] = {
     {"warp_fwd_variant", {-1}},  // -1 = auto, 0 = direct L1 gather, 1 = bulk-copy staged planes, 2 = channel-vectorised tiles
-    {"warp_bwd_variant", {-1}},  // -1 = auto, 0 = atomic scatter, 1 = tiled gather, 2 = channel-vectorised gather, 3 = deterministic (NDHWC gather lists)
+    {"warp_bwd_variant", {-1}},  // -1 = auto, 0 = atomic scatter, 1 = tiled gather, 2 = channel-vectorised gather, 3 = NDHWC gather lists (workspace), 4 = NDHWC tile gather (auto default), 0 on NDHWC = vector-atomic scatter
     {"tlerp_variant", {0}},
     {"bwd_rows", {8}},
     {"bwd_halo", {2}},
@@ -20,6 +20,8 @@ static Knob g_knobs[OPT_COUNT] = {
     {"fwd_halo", {2}},
     {"cvec_prefetch", {3}},      // L2 bulk-prefetch distance of the channel-vectorised kernels, in chunks (0 = off)
     {"bwd_chunk_mb", {0}},       // NDHWC scatter: process the batch in chunks of about this many MB (0 = whole batch)
+    {"ndhwc_bwd_rows", {0}},     // NDHWC tile gather: rows per tile (0 = auto, about 512 pixels per tile)
+    {"ndhwc_bwd_pf", {-1}},      // NDHWC tile gather: L2 prefetch distance in tiles (-1 = auto: 4 per SM, 0 = off)
 };
 
 int fail(int code, const char* fmt, ...) {

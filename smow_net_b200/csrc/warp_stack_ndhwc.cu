@@ -281,6 +281,259 @@ warp_bwd_ndhwc_apply_kernel(const float* __restrict__ gout, const float* __restr
   }
 }
 
+// ---- (T) tile gather: no workspace, no zero-fill, no atomics for displacements under one pixel ------------------
+// A CTA owns a tile of R x 32 pixels of one (pair, frame) plane of gx and writes it exactly once.
+//  stage  : the warped-slot gradient of the tile plus a one-pixel halo goes to shared memory with 16-byte
+//           asynchronous copies (cp.async, SASS LDGSTS: no register staging, the whole tile is in flight at once;
+//           halo pixels outside the image are zero-filled), 32 channels at a time;
+//  phase 0: meanwhile the clipped sample coordinates (ix, iy) and flow-gradient gates of the (R+2) x 34 sources
+//           are computed once per pixel (not per channel vector) into shared memory;
+//  phase 1: one thread per target pixel probes its 3x3 sources: source s covers target p with the separable
+//           weight wx*wy, wx = (px+1)-ix if ix >= px else ix-(px-1) — the very subtractions ATen's
+//           (ix_se-ix)/(ix-ix_nw) perform, so the weights are bit-identical; 9 weights per pixel (0 = no cover);
+//  phase 2: one thread per (target pixel, channel vector): gx = gout[pass] + sum_j w_j * staged[j] (9 LDS.128 at
+//           immediate offsets, fixed order => bit-reproducible), then the source-side work of the same pixel:
+//           4 taps of x against its own staged gradient -> flow-gradient sums, shuffle-reduced over the lanes of
+//           the pixel.  Global traffic per item = the forward kernel's (pass + 4 taps in, one vector out).
+// Taps farther than one pixel from their source (|tap - source| > 1 on either axis) are not visible to a 3x3
+// probe: warp_bwd_ndhwc_far_kernel (stream-ordered after the tile kernel) re-derives exactly that predicate
+// from the flow and adds them with vector reductions.  For sub-pixel flows it reads the flow and exits.
+// A zero weight still multiplies its staged neighbour: a non-finite gradient there propagates as NaN (0 * inf)
+// where ATen would not touch it.
+constexpr int TILE_W = 32, TILE_W2 = TILE_W + 2;
+
+__device__ __forceinline__ float cover_weight(float i, float pf, float pf_p1, float pf_m1) {
+  return i >= pf ? __fsub_rn(pf_p1, i) : __fsub_rn(i, pf_m1);      // > 0 iff the pixel is one of the two taps of i
+}
+// 16-byte async copy with zero-fill when !valid (src-size 0)
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(valid ? 16 : 0)
+               : "memory");
+}
+__host__ __device__ inline size_t tile_smem_bytes(int R, int LC) {
+  return ((size_t)(R + 2) * TILE_W2 * (LC + 1) + (size_t)R * TILE_W * 3) * 16 + (size_t)R * TILE_W * 8;
+}
+constexpr int ct_log2(int v) { return v <= 1 ? 0 : 1 + ct_log2(v >> 1); }
+
+// CT / WT: channel count and row width as compile-time constants (0 = runtime): global addresses are then one base
+// register plus immediates and the item index arithmetic is shifts by constants.
+template <int CT, int WT>
+__global__ void __launch_bounds__(256, 3)
+warp_bwd_ndhwc_tile_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
+                           int64_t sB, const float* __restrict__ flow, const float* __restrict__ xs,
+                           const float* __restrict__ ys, float* __restrict__ gx1, float* __restrict__ gx2,
+                           float* __restrict__ gflow, int C_, int H, int W_, int lshift_, int R, int tiles_x,
+                           int tiles_y, int wshift, int hshift) {
+  extern __shared__ float4 smem4[];
+  const int C = CT ? CT : C_, W = WT ? WT : W_;
+  const int lshift = CT ? (ct_log2(CT / 4) < 3 ? ct_log2(CT / 4) : 3) : lshift_;     // lanes per pixel LC = min(C/4, 8)
+  const int LC = 1 << lshift;
+  const int nchunks = (C >> 2) >> lshift;                                                // 32-channel chunks
+  const int HW = H * W;
+  float4* gws = smem4;                                    // [(R+2)][34][LC] staged warped-slot gradient
+  float4* sc = gws + (R + 2) * TILE_W2 * LC;              // [(R+2)][34]     source coordinates
+  float4* wt = sc + (R + 2) * TILE_W2;                    // [R*32][3]       probe weights
+  float2* gacc = reinterpret_cast<float2*>(wt + R * TILE_W * 3);   // [R*32] flow-gradient sums across chunks
+  int bid = blockIdx.x;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int ty = bid % tiles_y;
+  const int bt = bid / tiles_y;
+  const int h0 = ty * R, w0 = tx * TILE_W;
+  const int b = bt >> 1, t = bt & 1;
+  const int64_t fbase = ((int64_t)(b * 2) * 2 + t) * HW;
+  const float* gw = gout + ((int64_t)(b * 4 + 1 + t) * HW) * C;
+  const int n_stage = ((R + 2) * TILE_W2) << lshift;
+
+  auto stage = [&](int chunk) {
+    for (int i = threadIdx.x; i < n_stage; i += 256) {
+      const int sp = i >> lshift, lv = i & (LC - 1);
+      const int r = sp / TILE_W2, c = sp - r * TILE_W2;
+      const int h = h0 - 1 + r, w = w0 - 1 + c;
+      const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+      const float* g = gw + (ok ? ((int64_t)(h * W + w) * C + ((chunk << lshift) + lv) * 4) : 0);
+      cp_async16_zfill(gws + i, g, ok);
+    }
+    cp_async_commit();
+  };
+  stage(0);
+
+  // ---- phase 0: source coordinates ----
+  {
+    const float* fxp = flow + fbase;
+    const float* fyp = fxp + 2 * (int64_t)HW;
+    const float half_w = __fmul_rn((float)(W - 1), 0.5f), half_h = __fmul_rn((float)(H - 1), 0.5f);
+    for (int s = threadIdx.x; s < (R + 2) * TILE_W2; s += 256) {
+      const int r = s / TILE_W2;
+      const int w = w0 - 1 + s - r * TILE_W2, h = h0 - 1 + r;
+      float4 c = make_float4(-4.f, -4.f, 0.f, 0.f);            // outside the image: covers nothing
+      if (h >= 0 && h < H && w >= 0 && w < W) {
+        const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(fxp + h * W + w), __ldg(fyp + h * W + w), W, H);
+        c.x = __fadd_rn((float)fp.x0, fp.wx1);               // = ix exactly (wx1 = ix - floor(ix) is exact)
+        c.y = __fadd_rn((float)fp.y0, fp.wy1);
+        c.z = __fmul_rn(fp.gx_gate, half_w);
+        c.w = __fmul_rn(fp.gy_gate, half_h);
+      }
+      sc[s] = c;
+    }
+  }
+  __syncthreads();
+  // ---- phase 1: probe weights, one thread per target pixel ----
+  for (int pl = threadIdx.x; pl < R * TILE_W; pl += 256) {
+    const int hl = pl >> 5, wl = pl & 31;
+    const float pxf = (float)(w0 + wl), pyf = (float)(h0 + hl);
+    const float pxp = pxf + 1.f, pxm = pxf - 1.f, pyp = pyf + 1.f, pym = pyf - 1.f;
+    float wv[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const float4* row = sc + (hl + dy) * TILE_W2 + wl;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float2 c = *reinterpret_cast<const float2*>(row + dx);
+        const float wx = cover_weight(c.x, pxf, pxp, pxm), wy = cover_weight(c.y, pyf, pyp, pym);
+        wv[dy * 3 + dx] = (wx > 0.f && wy > 0.f) ? __fmul_rn(wx, wy) : 0.f;
+      }
+    }
+    wt[pl * 3 + 0] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    wt[pl * 3 + 1] = make_float4(wv[4], wv[5], wv[6], wv[7]);
+    wt[pl * 3 + 2] = make_float4(wv[8], 0.f, 0.f, 0.f);
+    gacc[pl] = make_float2(0.f, 0.f);
+  }
+  // ---- phase 2: one thread per (target pixel, channel vector), 32 channels at a time ----
+  const int n_items = (R * TILE_W) << lshift;
+  const int rowC = W * C;
+  const float* gpass = gout + ((int64_t)(b * 4 + (t ? 3 : 0)) * HW) * C;
+  const float* src = (t ? x2 : x1) + b * sB;
+  float* dst = (t ? gx2 : gx1) + b * sB;
+  const float inv_w = 1.f / (float)W, inv_h = 1.f / (float)H;
+  const int rstride = TILE_W2 * LC;                          // float4 per staged row
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    if (chunk > 0) { __syncthreads(); stage(chunk); }
+    cp_async_wait_all();
+    __syncthreads();
+    const int cbase = (chunk << lshift) * 4;
+    for (int base = 0; base < n_items; base += 256) {
+      const int it = base + threadIdx.x;
+      const int pl = it >> lshift, lv = it & (LC - 1);
+      const int hl = pl >> 5, wl = pl & 31;
+      const int h = h0 + hl, w = w0 + wl;
+      const bool live = it < n_items && h < H && w < W;
+      float gix = 0.f, giy = 0.f;
+      float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        const float4 wa = wt[pl * 3], wb = wt[pl * 3 + 1];
+        const float w8 = wt[pl * 3 + 2].x;
+        own = sc[(hl + 1) * TILE_W2 + wl + 1];
+        const float x0f = floorf(own.x), y0f = floorf(own.y);
+        const int x0 = (int)x0f, y0 = (int)y0f;
+        const float wx0 = __fsub_rn(__fadd_rn(x0f, 1.f), own.x), wx1 = __fsub_rn(own.x, x0f);
+        const float wy0 = __fsub_rn(__fadd_rn(y0f, 1.f), own.y), wy1 = __fsub_rn(own.y, y0f);
+        const bool x1ok = x0 + 1 <= W - 1, y1ok = y0 + 1 <= H - 1;
+        const int eo = (h * W + w) * C + cbase + lv * 4;
+        const float* xp = src + ((y0 * W + x0) * C + cbase + lv * 4);
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // global loads first (pass-through + the 4 taps of x), then the staged 3x3 gather
+        const float4 pass = __ldg(reinterpret_cast<const float4*>(gpass + eo));
+        const float4 xa = __ldg(reinterpret_cast<const float4*>(xp));
+        const float4 xb = x1ok ? __ldg(reinterpret_cast<const float4*>(xp + C)) : zero4;
+        const float4 xc = y1ok ? __ldg(reinterpret_cast<const float4*>(xp + rowC)) : zero4;
+        const float4 xd = (x1ok && y1ok) ? __ldg(reinterpret_cast<const float4*>(xp + rowC + C)) : zero4;
+        const float4* gc = gws + ((hl + 1) * TILE_W2 + wl + 1) * LC + lv;        // own pixel in the staged tile
+        const float wgt[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, w8};
+        float4 sum = zero4, g = zero4;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const float4 v = gc[(j / 3 - 1) * rstride + (j % 3 - 1) * LC];
+          if (j == 4) g = v;
+          sum.x = fmaf(wgt[j], v.x, sum.x); sum.y = fmaf(wgt[j], v.y, sum.y);
+          sum.z = fmaf(wgt[j], v.z, sum.z); sum.w = fmaf(wgt[j], v.w, sum.w);
+        }
+        *reinterpret_cast<float4*>(dst + eo) =
+            make_float4(__fadd_rn(pass.x, sum.x), __fadd_rn(pass.y, sum.y), __fadd_rn(pass.z, sum.z), __fadd_rn(pass.w, sum.w));
+        // source side (out-of-bounds taps were loaded as zeros: they add exact zeros, like ATen's skipped taps)
+        auto tap = [&](const float4& xv, float dgx, float dgy) {
+          const float dot = fmaf(xv.w, g.w, fmaf(xv.z, g.z, fmaf(xv.y, g.y, __fmul_rn(xv.x, g.x))));
+          gix = fmaf(dgx, dot, gix);
+          giy = fmaf(dgy, dot, giy);
+        };
+        tap(xa, -wy0, -wx0);
+        tap(xb, wy0, -wx1);
+        tap(xc, -wy1, wx0);
+        tap(xd, wy1, wx1);
+      }
+      for (int d = LC >> 1; d > 0; d >>= 1) {
+        gix += __shfl_xor_sync(0xffffffffu, gix, d);
+        giy += __shfl_xor_sync(0xffffffffu, giy, d);
+      }
+      if (live && lv == 0) {
+        if (nchunks > 1) {                                   // channels ascending across chunks, like one long sum
+          const float2 a = gacc[pl];
+          gix += a.x; giy += a.y;
+          gacc[pl] = make_float2(gix, giy);
+        }
+        if (chunk == nchunks - 1) {
+          const float a = __fmul_rn(own.z, gix), c = __fmul_rn(own.w, giy);
+          float* gf = gflow + fbase + h * W + w;
+          gf[0] = wshift >= 0 ? __fmul_rn(a, inv_w) : __fdiv_rn(a, (float)W);       // exact for power-of-two sizes
+          gf[2 * (int64_t)HW] = hshift >= 0 ? __fmul_rn(c, inv_h) : __fdiv_rn(c, (float)H);
+        }
+      }
+    }
+  }
+}
+
+// far taps of the tile gather: one lane per source pixel-frame finds them, the warp then adds them cooperatively
+__global__ void __launch_bounds__(256)
+warp_bwd_ndhwc_far_kernel(const float* __restrict__ gout, int64_t sB, const float* __restrict__ flow,
+                          const float* __restrict__ xs, const float* __restrict__ ys, float* __restrict__ gx1,
+                          float* __restrict__ gx2, int C, int H, int W, int q, int planes) {
+  const int HW = H * W;
+  const int64_t total = (int64_t)HW * planes, stride = (int64_t)gridDim.x * 256;
+  const int64_t rounds = (total + stride - 1) / stride;
+  const int lane = threadIdx.x & 31;
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (int64_t r = 0; r < rounds; ++r, i += stride) {
+    int mask = 0, bt = 0, p = 0, o_nw = 0;
+    float wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f;
+    if (i < total) {
+      bt = (int)(i / HW);
+      p = (int)(i - (int64_t)bt * HW);
+      const int h = p / W, w = p - h * W;
+      const int64_t fo = ((int64_t)(bt >> 1) * 4 + (bt & 1)) * HW + p;
+      const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
+      wx0 = fp.wx0; wx1 = fp.wx1; wy0 = fp.wy0; wy1 = fp.wy1;
+      o_nw = fp.y0 * W + fp.x0;
+      const int ex0 = fp.x0 - w, ey0 = fp.y0 - h;                   // tap offsets from the source: ex0, ex0+1 / ey0, ey0+1
+      const bool fx0 = ex0 < -1 || ex0 > 1, fx1 = ex0 + 1 < -1 || ex0 + 1 > 1;
+      const bool fy0 = ey0 < -1 || ey0 > 1, fy1 = ey0 + 1 < -1 || ey0 + 1 > 1;
+      const bool vx0 = wx0 > 0.f, vx1 = fp.x1ok && wx1 > 0.f, vy0 = wy0 > 0.f, vy1 = fp.y1ok && wy1 > 0.f;
+      mask = ((vx0 && vy0 && (fx0 || fy0)) ? 1 : 0) | ((vx1 && vy0 && (fx1 || fy0)) ? 2 : 0) |
+             ((vx0 && vy1 && (fx0 || fy1)) ? 4 : 0) | ((vx1 && vy1 && (fx1 || fy1)) ? 8 : 0);
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, mask != 0);
+    while (todo) {
+      const int sl = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int m = __shfl_sync(0xffffffffu, mask, sl), sbt = __shfl_sync(0xffffffffu, bt, sl);
+      const int sp = __shfl_sync(0xffffffffu, p, sl), so = __shfl_sync(0xffffffffu, o_nw, sl);
+      const float a0 = __shfl_sync(0xffffffffu, wx0, sl), a1 = __shfl_sync(0xffffffffu, wx1, sl);
+      const float b0 = __shfl_sync(0xffffffffu, wy0, sl), b1 = __shfl_sync(0xffffffffu, wy1, sl);
+      const int b = sbt >> 1, t = sbt & 1;
+      const float* gwp = gout + ((int64_t)(b * 4 + 1 + t) * HW + sp) * C;
+      float* dst = (t ? gx2 : gx1) + b * sB;
+      for (int v = lane; v < q; v += 32) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gwp + v * 4));
+        auto add = [&](int off, float wgt) {
+          atomicAdd(reinterpret_cast<float4*>(dst + (int64_t)off * C + v * 4), make_float4(wgt * g.x, wgt * g.y, wgt * g.z, wgt * g.w));
+        };
+        if (m & 1) add(so, __fmul_rn(a0, b0));
+        if (m & 2) add(so + 1, __fmul_rn(a1, b0));
+        if (m & 4) add(so + W, __fmul_rn(a0, b1));
+        if (m & 8) add(so + W + 1, __fmul_rn(a1, b1));
+      }
+    }
+  }
+}
+
 // ---- (S) vector-atomic scatter; both kernels are grid-stride over (plane, item) so that the "other family did
 // the work" exit costs a few hundred blocks, not one block per 256 items ----
 template <typename T>
@@ -427,6 +680,42 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
       warp_bwd_ndhwc_apply_kernel<<<grid, 256, 0, st>>>(gout, x1, x2, sB, flow, xs, ys, w, gx1, gx2, gflow, C, H, W, q, qs,
                                                         n_pf);
       launches += 4;
+    }
+    // (T) default: single-pass tile gather + far-tap pass (variant -1 / 4)
+    const int bv = option(OPT_WARP_BWD_VARIANT);
+    if (!gather && (bv < 0 || bv == 4) && shuffle) {
+      int R = option(OPT_NDHWC_BWD_ROWS);
+      if (R <= 0) R = 8;
+      if (R > H) R = H;
+      const int lshift = qs < 3 ? qs : 3;
+      const size_t smem = tile_smem_bytes(R, 1 << lshift);
+      if (smem <= 72 * 1024 && (int64_t)HW * C < (1ll << 31)) {
+        const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + R - 1) / R;
+        const unsigned tgrid = (unsigned)(tiles_x * tiles_y * 2 * B);
+#define SMOW_TILE_LAUNCH(CT, WT)                                                                                     \
+  do {                                                                                                               \
+    if (smem > 48 * 1024)                                                                                            \
+      cudaFuncSetAttribute(warp_bwd_ndhwc_tile_kernel<CT, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024); \
+    warp_bwd_ndhwc_tile_kernel<CT, WT><<<tgrid, 256, smem, st>>>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, C, \
+                                                                 H, W, lshift, R, tiles_x, tiles_y, ilog2_exact(W), \
+                                                                 ilog2_exact(H));                                    \
+  } while (0)
+        // compile-time (C, W) for the models' shapes (C = 16 / 32 at 128 x 128) and the sweep's; anything else is generic
+        bool done = false;
+#define SMOW_TILE_CASE(CT, WT) if (!done && C == CT && W == WT) { SMOW_TILE_LAUNCH(CT, WT); done = true; }
+        SMOW_TILE_CASE(16, 128) SMOW_TILE_CASE(32, 128) SMOW_TILE_CASE(64, 128) SMOW_TILE_CASE(128, 128)
+        SMOW_TILE_CASE(256, 128) SMOW_TILE_CASE(64, 64) SMOW_TILE_CASE(128, 64) SMOW_TILE_CASE(256, 64)
+        SMOW_TILE_CASE(64, 256) SMOW_TILE_CASE(128, 256) SMOW_TILE_CASE(256, 256)
+        if (!done) SMOW_TILE_LAUNCH(0, 0);
+#undef SMOW_TILE_CASE
+#undef SMOW_TILE_LAUNCH
+        const int64_t pf = (int64_t)HW * 2 * B;
+        const int fcap = device_info().sms * 16;
+        const int fgrid = (int)((pf + 255) / 256 < fcap ? (pf + 255) / 256 : fcap);
+        warp_bwd_ndhwc_far_kernel<<<fgrid, 256, 0, st>>>(gout, sB, flow, xs, ys, gx1, gx2, C, H, W, q, 2 * B);
+        count_launch(2);
+        return check_launch("warp_bwd_ndhwc_tile");
+      }
     }
     // (S) in batch chunks sized for the L2: a chunk's gx lines are still L2-resident when its vector reductions
     // arrive, so the read-modify-write never reaches HBM (one chunk for the models' per-GPU batches)

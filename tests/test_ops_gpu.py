@@ -281,10 +281,14 @@ CL3 = torch.channels_last_3d
 
 
 @pytest.mark.parametrize("case", [(4, 16, 128, 128, 0.3), (2, 32, 128, 128, 1.0), (2, 64, 64, 64, 8.0), (1, 8, 37, 52, 2.0),
-                                  (1, 256, 32, 32, 0.5), (2, 12, 40, 24, 3.0)])
-def test_warp_ndhwc_against_same_device_reference(case):
-    """channels_last_3d in -> channels_last_3d out (vector-gather forward, vector-atomic backward)."""
+                                  (1, 256, 32, 32, 0.5), (2, 12, 40, 24, 3.0), (1, 16, 5, 7, 2.5), (2, 32, 33, 128, 1.5),
+                                  (1, 4, 16, 1024, 0.8), (1, 512, 16, 16, 1.2)])
+@pytest.mark.parametrize("bv", [-1, 0])
+def test_warp_ndhwc_against_same_device_reference(case, bv, variants):
+    """channels_last_3d in -> channels_last_3d out (vector-gather forward; backward: tile gather + far pass by
+    default, vector-atomic scatter as variant 0 and for channel counts the gather does not take)."""
     B, C, H, W, sigma = case
+    _lib.set_option("warp_bwd_variant", bv)
     g = torch.Generator(device=DEV).manual_seed(C + H)
     x = torch.randn(B, C, 2, H, W, device=DEV, generator=g).contiguous(memory_format=CL3)
     flow = torch.randn(B, 2, 2, H, W, device=DEV, generator=g) * sigma
@@ -312,11 +316,34 @@ def test_warp_ndhwc_gather_backward_is_deterministic_and_matches_scatter(variant
     assert _lib.launch_count() - before == 1 + 6          # forward + (header, stat, list, apply, 2 early-exit scatter kernels)
     b = run_warp(x, flow, gout)
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
-    _lib.set_option("warp_bwd_variant", -1)
+    _lib.set_option("warp_bwd_variant", 0)
     before = _lib.launch_count()
     c = run_warp(x, flow, gout)
     assert _lib.launch_count() - before == 1 + 2          # forward + (init, scatter) for one L2-sized chunk
     assert float((a[1] - c[1]).abs().max()) <= 1e-5 and float((a[2] - c[2]).abs().max()) <= 1e-5 * _scale(a[2])
+
+
+@pytest.mark.parametrize("sigma", [0.3, 1.5])
+def test_warp_ndhwc_tile_gather_backward(sigma, variants):
+    """Default NDHWC backward: one tile-gather launch (+ the far-tap pass).  Without far taps (sub-pixel flow)
+    it is bit-reproducible and the flow gradient is bit-identical to the scatter kernel's (same per-pixel sums)."""
+    _lib.set_option("warp_bwd_variant", -1)
+    g = torch.Generator(device=DEV).manual_seed(77)
+    x = torch.randn(3, 32, 2, 128, 128, device=DEV, generator=g).contiguous(memory_format=CL3)
+    flow = torch.randn(3, 2, 2, 128, 128, device=DEV, generator=g) * sigma
+    gout = torch.randn(3, 32, 4, 128, 128, device=DEV, generator=g).contiguous(memory_format=CL3)
+    before = _lib.launch_count()
+    a = run_warp(x, flow, gout)
+    assert _lib.launch_count() - before == 1 + 2          # forward + (tile gather, far pass)
+    b = run_warp(x, flow, gout)
+    if sigma < 1.0:
+        assert torch.equal(a[1], b[1])
+    assert torch.equal(a[2], b[2])
+    _lib.set_option("warp_bwd_variant", 0)
+    c = run_warp(x, flow, gout)
+    assert torch.equal(a[2], c[2])
+    assert float((a[1] - c[1]).abs().max()) <= 1e-5
+    check_warp(a, torch_ref.warp_with_grads(x, flow, gout))
 
 
 def test_warp_ndhwc_bf16_forward():
