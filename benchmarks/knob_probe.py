@@ -33,7 +33,7 @@ for (B, C, H, sigma) in ((64, 32, 128, 0.3), (121, 16, 128, 0.3), (16, 16, 128, 
     _lib.set_option("warp_bwd_variant", 0)
     ms = t(bwd); res.append("scatter %.3f ms %.0f GB/s" % (ms, nbytes / ms / 1e6))
     _lib.set_option("warp_bwd_variant", -1)
-    for rows in (0, 2, 4, 6, 12):
+    for rows in (0, 8, 12, 16):
         _lib.set_option("ndhwc_bwd_rows", rows)
         ms = t(bwd); res.append("tile[R=%d] %.3f ms %.0f GB/s" % (rows, ms, nbytes / ms / 1e6))
     _lib.set_option("ndhwc_bwd_rows", 0)

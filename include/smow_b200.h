@@ -96,11 +96,13 @@ SMOW_API int smow_warp_pair_fwd(const void* x_t1, const void* x_t2, const float*
  *   gflow     = d(out)/d(flow) with the clamp mask (inclusive at ±1) and the
  *               border-clip mask.  gx needs no zero-fill by the caller.
  *   gout (B,C,4,H,W)  x (B,C,2,H,W)  gx (B,C,2,H,W)  gflow (B,2,2,H,W) fp32
- * workspace: optional caller-owned device scratch of at least smow_warp_bwd_workspace_bytes(B,H,W)
- *   bytes (uninitialised is fine; may be NULL).  With it the fp32 NDHWC backward runs as a
- *   deterministic gather (sample coordinates of every pixel are staged there once); without
- *   it, or when the flow's displacement range is too wide for the gather window, the vector-atomic
- *   scatter is used.  The library still never allocates.                                   */
+ * workspace: optional caller-owned device scratch (16-byte aligned; may be NULL).  The library still never
+ *   allocates.  fp32 NDHWC only:
+ *   - default backward (tile gather + far-tap pass): >= 64 bytes, zero-initialised ONCE by the caller and then
+ *     reused by every call on the same stream (do not share one block between concurrent streams).  Word 0
+ *     receives a per-call stamp when some source pixel has taps farther than one pixel away, so the far-tap
+ *     pass can exit immediately for sub-pixel flows; without a workspace that pass re-reads the flow.
+ *   - warp_bwd_variant = 3 (gather lists): smow_warp_bwd_workspace_bytes(B,H,W) bytes, uninitialised is fine.   */
 SMOW_API int64_t smow_warp_bwd_workspace_bytes(int B, int H, int W);
 SMOW_API int smow_warp_stack_bwd(const void* gout, const void* x, const float* flow,
                         const float* xs, const float* ys,

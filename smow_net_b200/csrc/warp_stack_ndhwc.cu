@@ -9,6 +9,7 @@
 // weighted gradients with ONE vector reduction each (red.global.add.v4.f32, SASS REDG.E.ADD.F32x4 — 4x fewer
 // L2 atomics than ATen's scalar scatter), and the flow-gradient partial sums of the q lanes of a pixel are
 // combined with warp shuffles.  Any displacement is handled uniformly (no tiles, no far pass).
+#include <atomic>
 #include <type_traits>
 #include "warp_stack_tiled.cuh"
 
@@ -298,12 +299,22 @@ warp_bwd_ndhwc_apply_kernel(const float* __restrict__ gout, const float* __restr
 // Taps farther than one pixel from their source (|tap - source| > 1 on either axis) are not visible to a 3x3
 // probe: warp_bwd_ndhwc_far_kernel (stream-ordered after the tile kernel) re-derives exactly that predicate
 // from the flow and adds them with vector reductions.  For sub-pixel flows it reads the flow and exits.
-// A zero weight still multiplies its staged neighbour: a non-finite gradient there propagates as NaN (0 * inf)
-// where ATen would not touch it.
+// With a caller workspace the tile kernel also publishes "some source has far taps" (an epoch stamp); the far pass
+// then exits at once for sub-pixel flows instead of re-reading the flow.
 constexpr int TILE_W = 32, TILE_W2 = TILE_W + 2;
 
 __device__ __forceinline__ float cover_weight(float i, float pf, float pf_p1, float pf_m1) {
   return i >= pf ? __fsub_rn(pf_p1, i) : __fsub_rn(i, pf_m1);      // > 0 iff the pixel is one of the two taps of i
+}
+// taps of the source pixel (w, h) the 3x3 probe of the tile kernel cannot see: in bounds, non-zero weight, and more
+// than one pixel away from the source on either axis.  bit 0 nw, 1 ne, 2 sw, 3 se.  Used by BOTH kernels.
+__device__ __forceinline__ int far_tap_mask(const Footprint& fp, int w, int h) {
+  const int ex0 = fp.x0 - w, ey0 = fp.y0 - h;                     // tap offsets from the source: ex0, ex0+1 / ey0, ey0+1
+  const bool fx0 = ex0 < -1 || ex0 > 1, fx1 = ex0 + 1 < -1 || ex0 + 1 > 1;
+  const bool fy0 = ey0 < -1 || ey0 > 1, fy1 = ey0 + 1 < -1 || ey0 + 1 > 1;
+  const bool vx0 = fp.wx0 > 0.f, vx1 = fp.x1ok && fp.wx1 > 0.f, vy0 = fp.wy0 > 0.f, vy1 = fp.y1ok && fp.wy1 > 0.f;
+  return ((vx0 && vy0 && (fx0 || fy0)) ? 1 : 0) | ((vx1 && vy0 && (fx1 || fy0)) ? 2 : 0) |
+         ((vx0 && vy1 && (fx0 || fy1)) ? 4 : 0) | ((vx1 && vy1 && (fx1 || fy1)) ? 8 : 0);
 }
 // 16-byte async copy with zero-fill when !valid (src-size 0)
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
@@ -323,7 +334,7 @@ warp_bwd_ndhwc_tile_kernel(const float* __restrict__ gout, const float* __restri
                            int64_t sB, const float* __restrict__ flow, const float* __restrict__ xs,
                            const float* __restrict__ ys, float* __restrict__ gx1, float* __restrict__ gx2,
                            float* __restrict__ gflow, int C_, int H, int W_, int lshift_, int R, int tiles_x,
-                           int tiles_y, int wshift, int hshift) {
+                           int tiles_y, int wshift, int hshift, int* __restrict__ far_flag, int epoch) {
   extern __shared__ float4 smem4[];
   const int C = CT ? CT : C_, W = WT ? WT : W_;
   const int lshift = CT ? (ct_log2(CT / 4) < 3 ? ct_log2(CT / 4) : 3) : lshift_;     // lanes per pixel LC = min(C/4, 8)
@@ -344,20 +355,25 @@ warp_bwd_ndhwc_tile_kernel(const float* __restrict__ gout, const float* __restri
   const float* gw = gout + ((int64_t)(b * 4 + 1 + t) * HW) * C;
   const int n_stage = ((R + 2) * TILE_W2) << lshift;
 
+  // staging walks (row, column) incrementally: 256 threads advance by 256/LC pixels per step, no divisions
+  const int adv = 256 >> lshift, adv_r = adv / TILE_W2, adv_c = adv - adv_r * TILE_W2;
   auto stage = [&](int chunk) {
+    const int sp0 = threadIdx.x >> lshift, lv = threadIdx.x & (LC - 1);
+    int r = sp0 / TILE_W2, c = sp0 - r * TILE_W2;
+    const float* g0 = gw + ((chunk << lshift) + lv) * 4;
     for (int i = threadIdx.x; i < n_stage; i += 256) {
-      const int sp = i >> lshift, lv = i & (LC - 1);
-      const int r = sp / TILE_W2, c = sp - r * TILE_W2;
       const int h = h0 - 1 + r, w = w0 - 1 + c;
       const bool ok = h >= 0 && h < H && w >= 0 && w < W;
-      const float* g = gw + (ok ? ((int64_t)(h * W + w) * C + ((chunk << lshift) + lv) * 4) : 0);
-      cp_async16_zfill(gws + i, g, ok);
+      cp_async16_zfill(gws + i, g0 + (ok ? (h * W + w) * C : 0), ok);
+      r += adv_r; c += adv_c;
+      if (c >= TILE_W2) { c -= TILE_W2; ++r; }
     }
     cp_async_commit();
   };
   stage(0);
 
   // ---- phase 0: source coordinates ----
+  bool found_far = false;
   {
     const float* fxp = flow + fbase;
     const float* fyp = fxp + 2 * (int64_t)HW;
@@ -372,10 +388,13 @@ warp_bwd_ndhwc_tile_kernel(const float* __restrict__ gout, const float* __restri
         c.y = __fadd_rn((float)fp.y0, fp.wy1);
         c.z = __fmul_rn(fp.gx_gate, half_w);
         c.w = __fmul_rn(fp.gy_gate, half_h);
+        if (far_flag != nullptr && far_tap_mask(fp, w, h) != 0) found_far = true;
       }
       sc[s] = c;
     }
   }
+  // tell the far pass (stream-ordered after this kernel) that it has work; every writer stores the same epoch
+  if (found_far) *far_flag = epoch;
   __syncthreads();
   // ---- phase 1: probe weights, one thread per target pixel ----
   for (int pl = threadIdx.x; pl < R * TILE_W; pl += 256) {
@@ -439,13 +458,15 @@ warp_bwd_ndhwc_tile_kernel(const float* __restrict__ gout, const float* __restri
         const float4 xd = (x1ok && y1ok) ? __ldg(reinterpret_cast<const float4*>(xp + rowC + C)) : zero4;
         const float4* gc = gws + ((hl + 1) * TILE_W2 + wl + 1) * LC + lv;        // own pixel in the staged tile
         const float wgt[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, w8};
-        float4 sum = zero4, g = zero4;
+        const float4 g = gc[0];                              // own pixel: the source-side gradient
+        float4 sum = make_float4(wgt[4] * g.x, wgt[4] * g.y, wgt[4] * g.z, wgt[4] * g.w);
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
-          const float4 v = gc[(j / 3 - 1) * rstride + (j % 3 - 1) * LC];
-          if (j == 4) g = v;
-          sum.x = fmaf(wgt[j], v.x, sum.x); sum.y = fmaf(wgt[j], v.y, sum.y);
-          sum.z = fmaf(wgt[j], v.z, sum.z); sum.w = fmaf(wgt[j], v.w, sum.w);
+          if (j != 4 && wgt[j] != 0.f) {                     // a zero weight costs no shared-memory wavefront
+            const float4 v = gc[(j / 3 - 1) * rstride + (j % 3 - 1) * LC];
+            sum.x = fmaf(wgt[j], v.x, sum.x); sum.y = fmaf(wgt[j], v.y, sum.y);
+            sum.z = fmaf(wgt[j], v.z, sum.z); sum.w = fmaf(wgt[j], v.w, sum.w);
+          }
         }
         *reinterpret_cast<float4*>(dst + eo) =
             make_float4(__fadd_rn(pass.x, sum.x), __fadd_rn(pass.y, sum.y), __fadd_rn(pass.z, sum.z), __fadd_rn(pass.w, sum.w));
@@ -485,7 +506,9 @@ warp_bwd_ndhwc_tile_kernel(const float* __restrict__ gout, const float* __restri
 __global__ void __launch_bounds__(256)
 warp_bwd_ndhwc_far_kernel(const float* __restrict__ gout, int64_t sB, const float* __restrict__ flow,
                           const float* __restrict__ xs, const float* __restrict__ ys, float* __restrict__ gx1,
-                          float* __restrict__ gx2, int C, int H, int W, int q, int planes) {
+                          float* __restrict__ gx2, int C, int H, int W, int q, int planes,
+                          const int* __restrict__ far_flag, int epoch) {
+  if (far_flag != nullptr && *far_flag != epoch) return;       // the tile kernel saw no far tap in this launch
   const int HW = H * W;
   const int64_t total = (int64_t)HW * planes, stride = (int64_t)gridDim.x * 256;
   const int64_t rounds = (total + stride - 1) / stride;
@@ -502,12 +525,7 @@ warp_bwd_ndhwc_far_kernel(const float* __restrict__ gout, int64_t sB, const floa
       const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
       wx0 = fp.wx0; wx1 = fp.wx1; wy0 = fp.wy0; wy1 = fp.wy1;
       o_nw = fp.y0 * W + fp.x0;
-      const int ex0 = fp.x0 - w, ey0 = fp.y0 - h;                   // tap offsets from the source: ex0, ex0+1 / ey0, ey0+1
-      const bool fx0 = ex0 < -1 || ex0 > 1, fx1 = ex0 + 1 < -1 || ex0 + 1 > 1;
-      const bool fy0 = ey0 < -1 || ey0 > 1, fy1 = ey0 + 1 < -1 || ey0 + 1 > 1;
-      const bool vx0 = wx0 > 0.f, vx1 = fp.x1ok && wx1 > 0.f, vy0 = wy0 > 0.f, vy1 = fp.y1ok && wy1 > 0.f;
-      mask = ((vx0 && vy0 && (fx0 || fy0)) ? 1 : 0) | ((vx1 && vy0 && (fx1 || fy0)) ? 2 : 0) |
-             ((vx0 && vy1 && (fx0 || fy1)) ? 4 : 0) | ((vx1 && vy1 && (fx1 || fy1)) ? 8 : 0);
+      mask = far_tap_mask(fp, w, h);
     }
     unsigned todo = __ballot_sync(0xffffffffu, mask != 0);
     while (todo) {
@@ -685,20 +703,24 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
     const int bv = option(OPT_WARP_BWD_VARIANT);
     if (!gather && (bv < 0 || bv == 4) && shuffle) {
       int R = option(OPT_NDHWC_BWD_ROWS);
-      if (R <= 0) R = 8;
-      if (R > H) R = H;
       const int lshift = qs < 3 ? qs : 3;
+      if (R <= 0) R = lshift == 3 ? 8 : 12;
+      if (R > H) R = H;
       const size_t smem = tile_smem_bytes(R, 1 << lshift);
       if (smem <= 72 * 1024 && (int64_t)HW * C < (1ll << 31)) {
         const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + R - 1) / R;
         const unsigned tgrid = (unsigned)(tiles_x * tiles_y * 2 * B);
+        // optional caller workspace (>= 64 B, 16 B aligned): word 0 carries the far-tap epoch stamp of this call
+        static std::atomic<int> g_epoch{0};
+        int* far_flag = (ws != nullptr && ws_bytes >= 64 && aligned16(ws)) ? reinterpret_cast<int*>(ws) : nullptr;
+        const int epoch = g_epoch.fetch_add(1, std::memory_order_relaxed) + 1;
 #define SMOW_TILE_LAUNCH(CT, WT)                                                                                     \
   do {                                                                                                               \
     if (smem > 48 * 1024)                                                                                            \
       cudaFuncSetAttribute(warp_bwd_ndhwc_tile_kernel<CT, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024); \
     warp_bwd_ndhwc_tile_kernel<CT, WT><<<tgrid, 256, smem, st>>>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, C, \
                                                                  H, W, lshift, R, tiles_x, tiles_y, ilog2_exact(W), \
-                                                                 ilog2_exact(H));                                    \
+                                                                 ilog2_exact(H), far_flag, epoch);                   \
   } while (0)
         // compile-time (C, W) for the models' shapes (C = 16 / 32 at 128 x 128) and the sweep's; anything else is generic
         bool done = false;
@@ -712,7 +734,7 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
         const int64_t pf = (int64_t)HW * 2 * B;
         const int fcap = device_info().sms * 16;
         const int fgrid = (int)((pf + 255) / 256 < fcap ? (pf + 255) / 256 : fcap);
-        warp_bwd_ndhwc_far_kernel<<<fgrid, 256, 0, st>>>(gout, sB, flow, xs, ys, gx1, gx2, C, H, W, q, 2 * B);
+        warp_bwd_ndhwc_far_kernel<<<fgrid, 256, 0, st>>>(gout, sB, flow, xs, ys, gx1, gx2, C, H, W, q, 2 * B, far_flag, epoch);
         count_launch(2);
         return check_launch("warp_bwd_ndhwc_tile");
       }

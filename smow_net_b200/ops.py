@@ -148,12 +148,23 @@ def tlerp_bwd_bytes(B, Cs, hw, s):
     return B * 6 * Cs * hw * s
 
 
+_FLAG_WS = {}
+
+
 def _bwd_workspace(lib, like, layout, B, H, W):
-    """Scratch for the deterministic NDHWC gather backward (caller-owned: the C ABI never allocates)."""
-    if layout != _lib.NDHWC or like.dtype != torch.float32 or _lib.get_option("warp_bwd_variant") != 3:
+    """Caller-owned scratch of the NDHWC fp32 backward (the C ABI never allocates): the gather-list variant (3) needs
+    per-pixel lists; the default tile gather only a 64-byte word block for its far-tap stamp — zero-initialised once
+    and cached per (device, stream), because two launches in flight must not share a stamp."""
+    if layout != _lib.NDHWC or like.dtype != torch.float32:
         return None, 0
-    n = int(lib.smow_warp_bwd_workspace_bytes(B, H, W))
-    return torch.empty(n, dtype=torch.uint8, device=like.device), n
+    if _lib.get_option("warp_bwd_variant") == 3:
+        n = int(lib.smow_warp_bwd_workspace_bytes(B, H, W))
+        return torch.empty(n, dtype=torch.uint8, device=like.device), n
+    key = (like.device.index, torch.cuda.current_stream(like.device).cuda_stream)
+    ws = _FLAG_WS.get(key)
+    if ws is None:
+        ws = _FLAG_WS[key] = torch.zeros(64, dtype=torch.uint8, device=like.device)
+    return ws, 64
 
 
 # ----------------------------------------------------------------------------- A1: warp + stack

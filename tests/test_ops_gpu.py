@@ -326,7 +326,7 @@ def test_warp_ndhwc_gather_backward_is_deterministic_and_matches_scatter(variant
 @pytest.mark.parametrize("sigma", [0.3, 1.5])
 def test_warp_ndhwc_tile_gather_backward(sigma, variants):
     """Default NDHWC backward: one tile-gather launch (+ the far-tap pass).  Without far taps (sub-pixel flow)
-    it is bit-reproducible and the flow gradient is bit-identical to the scatter kernel's (same per-pixel sums)."""
+    it is bit-reproducible; it agrees with the vector-atomic scatter kernel."""
     _lib.set_option("warp_bwd_variant", -1)
     g = torch.Generator(device=DEV).manual_seed(77)
     x = torch.randn(3, 32, 2, 128, 128, device=DEV, generator=g).contiguous(memory_format=CL3)
@@ -341,7 +341,7 @@ def test_warp_ndhwc_tile_gather_backward(sigma, variants):
     assert torch.equal(a[2], b[2])
     _lib.set_option("warp_bwd_variant", 0)
     c = run_warp(x, flow, gout)
-    assert torch.equal(a[2], c[2])
+    assert float((a[2] - c[2]).abs().max()) <= 1e-5 * _scale(a[2])
     assert float((a[1] - c[1]).abs().max()) <= 1e-5
     check_warp(a, torch_ref.warp_with_grads(x, flow, gout))
 
