@@ -41,14 +41,15 @@ def parse():
     ap.add_argument("--model", default=MODEL, choices=["lw", "s"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strict-fp32", action="store_true", help="disable cuDNN TF32 convolutions")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying its CUDA graph")
     ap.add_argument("--profile-step", action="store_true",
                     help="ncu helper: warm up, then run --steps steps between cudaProfilerStart/Stop and exit")
     return ap.parse_args()
 
 
-def config(args, world):
+def config(args, world, launch_mode="eager"):
     name = "SMOW_Net_LW" if args.model == "lw" else "SMOW_Net"
-    return {"workload": "%s forward+backward (BCE-Dice loss), batch %d per GPU, 256x256 synthetic pairs "
+    return {"launch": launch_mode, "workload": "%s forward+backward (BCE-Dice loss), batch %d per GPU, 256x256 synthetic pairs "
                         "(BASELINE.json configs[1])" % (name, args.batch),
             "global_batch": args.batch * world, "image_size": 256,
             "parallelism": "dp%d (DDP, NCCL gradient all-reduce)" % world if world > 1 else "single GPU",
@@ -135,15 +136,39 @@ def main():
     from smow_net_b200.runtime import launch, step as S, synthetic
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    if world > 1 and not args.no_graph:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")      # NCCL inside a CUDA graph: no watchdog aborts
     rank, local_rank, world, device = launch.init_distributed()
     if args.strict_fp32:
         torch.backends.cudnn.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
     synthetic.seed_everything(2022, rank)
-    model = launch.wrap_ddp(launch.build_model(args.model, device), device, world).train()
+    if world > 1 and not args.no_graph:
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):                                       # DDP must be built off the default stream
+            model = launch.wrap_ddp(launch.build_model(args.model, device), device, world).train()
+        torch.cuda.current_stream().wait_stream(side)
+    else:
+        model = launch.wrap_ddp(launch.build_model(args.model, device), device, world).train()
     B = args.batch
     a, b, y = synthetic.make_batch(B, device=device, seed=2022 + rank)
     ha, hb, hy = synthetic.make_batch(B, seed=3033 + rank, pin=True)
+
+    # the timed step: one replay of the whole-step CUDA graph (runtime/graph.py), or the eager launch loop
+    launch_mode, gs = "eager", None
+    if not args.no_graph and not args.profile_step:
+        try:
+            from smow_net_b200.runtime import graph as G
+            gs = G.GraphedStep(model, a, b, y, warmup=11 if world > 1 else max(3, args.warmup))
+            launch_mode = "cuda-graph replay of the whole step (one cudaGraphLaunch per step)"
+        except Exception as e:                                              # e.g. a collective that cannot be captured
+            gs, launch_mode = None, "eager (graph capture failed: %s)" % (str(e).splitlines()[0][:120],)
+    ok = torch.tensor([1 if gs is not None else 0], device=device)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                           # every rank must run the same mode
+        if int(ok.item()) == 0:
+            gs = None
+    step = (lambda: gs()) if gs is not None else (lambda: S.fwd_bwd(model, a, b, y))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -153,7 +178,7 @@ def main():
 
     # ---------------- device-resident leg (value) ----------------
     for _ in range(max(3, args.warmup)):
-        S.fwd_bwd(model, a, b, y)
+        step()
     sync_all()
     if args.profile_step:      # for `ncu --profile-from-start off`: exactly the timed steps are captured
         torch.cuda.profiler.start()
@@ -168,20 +193,21 @@ def main():
         clocks.start()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ops.kernel_timer() as kt:
-        e0.record()
-        for _ in range(args.steps):
-            S.fwd_bwd(model, a, b, y)
-        e1.record()
-        sync_all()
-    launches = _lib.launch_count() - l0
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    launches = gs.hot_path_launches * args.steps if gs is not None else _lib.launch_count() - l0
     ms = launch.max_over_ranks(e0.elapsed_time(e1), device, world)
     value = B * world * args.steps / (ms * 1e-3)
 
     # ---------------- host-buffer leg (e2e) ----------------
     def e2e_step():
+        if gs is not None:                                     # H2D into the graph's static input buffers, replay
+            return float(gs(ha, hb, hy).item())                # D2H read of the loss every step
         da, db, dy = ha.to(device, non_blocking=True), hb.to(device, non_blocking=True), hy.to(device, non_blocking=True)
-        return float(S.fwd_bwd(model, da, db, dy).item())      # D2H read of the loss every step
+        return float(S.fwd_bwd(model, da, db, dy).item())
     for _ in range(3):
         e2e_step()
     sync_all()
@@ -196,14 +222,21 @@ def main():
     ms_e2e = launch.max_over_ranks(max(e2.elapsed_time(e3), wall * 1e3), device, world)
     clk = clocks.stop() if rank == 0 else None
     e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
+    # per-launch CUDA-event timing of the hand-written kernels inside real (eager) steps, for the roofline object:
+    # events cannot be recorded inside a graph replay, so these steps run outside the timed regions
+    n_kt = min(5, args.steps)
+    with ops.kernel_timer() as kt:
+        for _ in range(n_kt):
+            S.fwd_bwd(model, a, b, y)
+        sync_all()
     h2d = sum(t.numel() * t.element_size() for t in (ha, hb, hy))
 
     if rank == 0:
         peak, peak_src = measured_peak()
         summ = kt.summary()
-        kernels = {k: {"calls_per_step": v["calls"] / args.steps, "ms_per_call": v["ms"] / v["calls"],
+        kernels = {k: {"calls_per_step": v["calls"] / n_kt, "ms_per_call": v["ms"] / v["calls"],
                        "algorithmic_GB_per_s": v["gbps"], "frac_of_peak": v["gbps"] / peak,
-                       "ms_per_step": v["ms"] / args.steps} for k, v in summ.items()}
+                       "ms_per_step": v["ms"] / n_kt} for k, v in summ.items()}
         dom = max(summ, key=lambda k: summ[k]["ms"])
         roof = {"bound": "hbm", "kernel": dom, "achieved": summ[dom]["gbps"], "peak": peak, "unit": "GB/s",
                 "frac": summ[dom]["gbps"] / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
@@ -211,7 +244,7 @@ def main():
                 "note": "in-step launches: operands were just produced, so part of the traffic is L2-resident; "
                         "HBM-cold figures are in profiles/ (benchmarks/sweep_warp.py)",
                 "all_kernels": kernels,
-                "hot_path_share_of_step": sum(v["ms"] for v in summ.values()) / (ms if ms > 0 else 1)}
+                "hot_path_share_of_step": sum(v["ms"] for v in summ.values()) / n_kt / (ms / args.steps if ms > 0 else 1)}
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_model
@@ -222,11 +255,22 @@ def main():
         print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": config(args, world), "roofline": roof, "cpu_baseline": cb,
+                          "config": config(args, world, launch_mode), "roofline": roof, "cpu_baseline": cb,
                           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                                   "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
                           "gpu_launches": launches, "clocks": clk}))
     if world > 1:
+        if gs is not None:
+            # a captured graph keeps NCCL work objects alive and ProcessGroupNCCL's teardown then waits for ever:
+            # drop the graph, drain the device, agree that everybody is done and leave without the teardown
+            del step, gs
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

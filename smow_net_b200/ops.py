@@ -160,6 +160,10 @@ def _bwd_workspace(lib, like, layout, B, H, W):
     if _lib.get_option("warp_bwd_variant") == 3:
         n = int(lib.smow_warp_bwd_workspace_bytes(B, H, W))
         return torch.empty(n, dtype=torch.uint8, device=like.device), n
+    if torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture the block must belong to the graph's private pool (a cached tensor from outside
+        # could be freed under the graph): one 64-byte allocation + memset node per captured backward
+        return torch.zeros(64, dtype=torch.uint8, device=like.device), 64
     key = (like.device.index, torch.cuda.current_stream(like.device).cuda_stream)
     ws = _FLAG_WS.get(key)
     if ws is None:

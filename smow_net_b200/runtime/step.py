@@ -21,9 +21,15 @@ def clip_gradient_(params, clip):
         torch._foreach_clamp_max_(grads, clip)
 
 
-def make_optimizer(model, lr=1e-4, weight_decay=1e-4):
+def make_optimizer(model, lr=1e-4, weight_decay=1e-4, capturable=False):
+    """AdamW(1e-4, wd 1e-4) as train.py:127; fused multi-tensor kernel on CUDA.  capturable=True keeps the step count
+    and the learning rate on the device so the step can live inside a CUDA graph (runtime/graph.py) while the
+    scheduler keeps updating the rate from the host."""
     params = [p for p in model.parameters() if p.requires_grad]
     fused = bool(params) and all(p.is_cuda for p in params)    # one multi-tensor kernel instead of ~10 per tensor
+    if capturable and fused:
+        lr = torch.tensor(float(lr), device=params[0].device)
+        return torch.optim.AdamW(params, lr, weight_decay=weight_decay, fused=True, capturable=True)
     return torch.optim.AdamW(params, lr, weight_decay=weight_decay, fused=fused)
 
 

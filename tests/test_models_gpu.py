@@ -91,3 +91,42 @@ def test_tiled_inference_matches_per_crop_calls():
         direct = model(ta[:, :, 256:512, 512:768].contiguous(), tb[:, :, 256:512, 512:768].contiguous())
     assert full.shape == (1, 1, 512, 768)
     assert float((full[:, :, 256:512, 512:768] - direct).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("with_optimizer", [False, True])
+def test_graphed_step_replays_the_eager_step(with_optimizer):
+    """runtime/graph.py: one CUDA graph of forward + loss + backward (+ clip + AdamW) gives the eager step's loss and
+    gradients on fresh inputs, and the hand-written kernels are inside the graph."""
+    from smow_net_b200.runtime import graph as G, step as S, synthetic
+    torch.manual_seed(5)
+    model = helpers.seeded_model("lw", device=DEV).train()
+    S.freeze_unused(model)
+    a, b, y = synthetic.make_batch(2, device=DEV, seed=11)
+    a2, b2, y2 = synthetic.make_batch(2, device=DEV, seed=12)
+    twin = helpers.seeded_model("lw", device=DEV).train()
+    S.freeze_unused(twin)
+    opt = S.make_optimizer(model, capturable=True) if with_optimizer else None
+    opt2 = S.make_optimizer(twin) if with_optimizer else None
+    gs = G.GraphedStep(model, a, b, y, optimizer=opt, warmup=2)
+    assert gs.hot_path_launches >= 14
+    if with_optimizer:
+        # the twin takes the same number of eager steps on the same batches (capture itself executes nothing)
+        for _ in range(2):
+            S.train_step(twin, opt2, None, a, b, y)
+        loss_g = float(gs(a2, b2, y2).detach())
+        loss_e = float(S.train_step(twin, opt2, None, a2, b2, y2).detach())
+        assert abs(loss_g - loss_e) <= 2e-3 * max(1.0, abs(loss_e))
+        pa, pb = dict(model.named_parameters()), dict(twin.named_parameters())
+        worst = max(float((pa[k] - pb[k]).abs().max()) for k in pa)
+        assert worst <= 5e-3
+    else:
+        twin.load_state_dict(model.state_dict())       # BatchNorm statistics moved during warm-up + capture
+        loss_g = float(gs(a2, b2, y2).detach())
+        loss_e = float(S.fwd_bwd(twin, a2, b2, y2).detach())
+        assert abs(loss_g - loss_e) <= 1e-5 * max(1.0, abs(loss_e))
+        ga = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        gb = {k: p.grad for k, p in twin.named_parameters() if p.grad is not None}
+        assert ga.keys() == gb.keys()
+        for k in ga:
+            scale = max(1.0, float(gb[k].abs().max()))
+            assert float((ga[k] - gb[k]).abs().max()) <= 2e-4 * scale, k
