@@ -13,12 +13,84 @@ import torch
 import torch.nn as nn
 
 
-def cyclic_frame_mix(frames5d, shared, own):
-    """frames5d: (B,C,4,H,W); shared: module; own: list of 4 modules (own[k] acts on frame k)."""
+def _cyclic_frame_mix_composed(frames5d, shared, own):
+    """The reference's own composition (models/SMOW_Net.py:121-139): slice, ten 1x1x1 convs, adds, concat."""
     parts = [frames5d[:, :, k:k + 1] for k in range(4)]
     kept = [shared(p) for p in parts]
     lent = [m(p) for m, p in zip(own, parts)]
     return torch.cat([kept[j] + lent[(j + 1) % 4] for j in range(4)], dim=2)
+
+
+def _mix_matrix(conv):
+    """(Cin, Cout) matrix of a 1x1x1 Conv3d (weight is Cout x Cin) or ConvTranspose3d (weight is Cin x Cout)."""
+    w = conv.weight[:, :, 0, 0, 0]
+    return w if isinstance(conv, nn.ConvTranspose3d) else w.t()
+
+
+class _CyclicMixGemm(torch.autograd.Function):
+    """Row N4: the frame mix as plain GEMMs on the channels-last tensor, no slicing copies, no concat.
+
+    In NDHWC memory a frame of one pair is a dense (HW, C) matrix, so with X = (B, 4, HW, Cin):
+        Y           = X @ W_shared                      one GEMM over all four frames
+        Y[:, j]    += X[:, (j+1) % 4] @ W_own[j+1]      four strided-batched GEMMs accumulating in place
+    and the backward is the transposed set.  The 1x1x1 convolutions this replaces ran on cuDNN under
+    torch.backends.cudnn.allow_tf32, so that flag also decides whether these GEMMs may use TF32."""
+
+    @staticmethod
+    def forward(ctx, x5, w_shared, w0, w1, w2, w3, bias):
+        B, Cin, T, H, W = x5.shape
+        X = x5.permute(0, 2, 3, 4, 1).reshape(B, T, H * W, Cin)          # a view: x5 is channels_last_3d
+        ws = (w0, w1, w2, w3)
+        Cout = w_shared.shape[1]
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
+        try:
+            Y = torch.mm(X.view(-1, Cin), w_shared).view(B, T, H * W, Cout)
+            for j in range(4):
+                k = (j + 1) % 4
+                Y[:, j].baddbmm_(X[:, k], ws[k].unsqueeze(0).expand(B, Cin, Cout))
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+        if bias is not None:                                                 # (4, Cout): shared bias + own[j+1] bias
+            Y.add_(bias.view(1, T, 1, Cout))
+        ctx.save_for_backward(X, w_shared, w0, w1, w2, w3)
+        ctx.has_bias = bias is not None
+        ctx.dims = (B, Cin, Cout, T, H, W)
+        return Y.view(B, T, H, W, Cout).permute(0, 4, 1, 2, 3)
+
+    @staticmethod
+    def backward(ctx, gy5):
+        X, w_shared, w0, w1, w2, w3 = ctx.saved_tensors
+        B, Cin, Cout, T, H, W = ctx.dims
+        ws = (w0, w1, w2, w3)
+        G = gy5.contiguous(memory_format=torch.channels_last_3d).permute(0, 2, 3, 4, 1).reshape(B, T, H * W, Cout)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
+        try:
+            G2, X2 = G.view(-1, Cout), X.view(-1, Cin)
+            gX = torch.mm(G2, w_shared.t()).view(B, T, H * W, Cin)
+            gws = [None] * 4
+            for j in range(4):
+                k = (j + 1) % 4
+                gX[:, k].baddbmm_(G[:, j], ws[k].t().unsqueeze(0).expand(B, Cout, Cin))
+                gws[k] = torch.bmm(X[:, k].transpose(1, 2), G[:, j]).sum(0)
+            g_shared = torch.mm(X2.t(), G2)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+        gbias = G.sum(dim=(0, 2)) if ctx.has_bias else None               # (4, Cout)
+        return gX.view(B, T, H, W, Cin).permute(0, 4, 1, 2, 3), g_shared, gws[0], gws[1], gws[2], gws[3], gbias
+
+
+def cyclic_frame_mix(frames5d, shared, own):
+    """frames5d: (B,C,4,H,W); shared: module; own: list of 4 modules (own[k] acts on frame k)."""
+    if not (frames5d.is_cuda and frames5d.shape[2] == 4 and frames5d.dtype == torch.float32
+            and frames5d.is_contiguous(memory_format=torch.channels_last_3d)):
+        return _cyclic_frame_mix_composed(frames5d, shared, own)
+    bias = None
+    if shared.bias is not None:
+        # out[j] = shared(f_j) + own[j+1](f_{j+1}): frame j carries the shared bias plus the bias of own[(j+1) % 4]
+        bias = torch.stack([shared.bias + own[(j + 1) % 4].bias for j in range(4)])
+    return _CyclicMixGemm.apply(frames5d, _mix_matrix(shared), *[_mix_matrix(m) for m in own], bias)
 
 
 def _identity_1x1(conv):

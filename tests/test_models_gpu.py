@@ -130,3 +130,29 @@ def test_graphed_step_replays_the_eager_step(with_optimizer):
         for k in ga:
             scale = max(1.0, float(gb[k].abs().max()))
             assert float((ga[k] - gb[k]).abs().max()) <= 2e-4 * scale, k
+
+
+@pytest.mark.parametrize("kind", ["conv", "deconv_bias"])
+def test_cyclic_frame_mix_gemm_matches_the_composed_reference(kind):
+    """Row N4: the GEMM formulation of the frame mix (models/blocks.py) equals the reference's composition of slices,
+    1x1x1 convolutions, adds and a concat — outputs, input gradient and all ten parameter gradients."""
+    from smow_net_b200.models import blocks
+    torch.manual_seed(3)
+    cin, cout = (24, 24) if kind == "conv" else (20, 12)
+    mk = (lambda: torch.nn.Conv3d(cin, cout, 1, bias=False)) if kind == "conv" else \
+         (lambda: torch.nn.ConvTranspose3d(cin, cout, 1, bias=True))
+    mods = [mk().to(DEV) for _ in range(5)]
+    x = torch.randn(3, cin, 4, 9, 7, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    g = torch.randn(3, cout, 4, 9, 7, device=DEV)
+    res = []
+    for fn in (blocks.cyclic_frame_mix, blocks._cyclic_frame_mix_composed):
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        xi = x.clone(memory_format=torch.preserve_format).requires_grad_(True)
+        y = fn(xi, mods[4], mods[:4])
+        y.backward(g)
+        res.append([y.detach(), xi.grad] + [p.grad.clone() for m in mods for p in m.parameters()])
+    assert res[0][0].is_contiguous(memory_format=torch.channels_last_3d)
+    for a, b in zip(*res):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(b.abs().max()))
