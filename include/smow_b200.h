@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SMOW_ABI_VERSION 2
+#define SMOW_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SMOW_API __attribute__((visibility("default")))
@@ -141,6 +141,28 @@ SMOW_API int smow_tlerp_cat_bwd(const void* gcat, void* gskip,
 SMOW_API int smow_tlerp_pair_cat_bwd(const void* gcat, void* gskip_t1, void* gskip_t2,
                             int B, int Cd, int Cs, int64_t hw,
                             int dtype, int layout, void* stream);
+
+/* ---- N2: semantic tokenizer (the sole consumer of the warped stack) ---------------------------
+ * Replaces, per frame k of the stack, models/SMOW_Net.py:176-187 (= models/SMOW_Net_LW.py:195-206):
+ *   spatial_attention = conv_a(x[:, :, k])  (1x1, C -> 8)  -> view(b, 8, H*W) -> softmax(dim=-1)
+ *   tokens_k          = einsum('bln,bcn->blc', spatial_attention, x[:, :, k].view(b, c, H*W))
+ * for all four frames in one pass over the stack (plus a small chunk-combine launch).  The
+ * positional embedding and the concat of the four token sets stay with the caller.
+ *   x       (B,C,4,H,W) fp32, layout SMOW_NDHWC only; C/4 a power of two <= 32
+ *   wa      (8,C) = conv_a.weight[:, :, 0, 0]     ba (8) = conv_a.bias
+ *   tokens  (B,4,8,C) out                          stats (B,4,16) out: per token max logit | 1/sum exp
+ *   workspace: smow_tokenizer_workspace_bytes(B,C,hw) bytes, 16-byte aligned, uninitialised.
+ * Backward: gx (B,C,4,H,W) NDHWC = d loss / d x through both the attention and the pooling,
+ *   gwa (8,C), gba (8) overwritten (not accumulated); tokens / stats are the forward's outputs.
+ * All sums run in a fixed order: results are bit-reproducible.                                  */
+SMOW_API int64_t smow_tokenizer_workspace_bytes(int B, int C, int64_t hw);
+SMOW_API int smow_tokenizer_fwd(const void* x, const float* wa, const float* ba,
+                       float* tokens, float* stats, int B, int C, int64_t hw,
+                       int dtype, int layout, void* workspace, int64_t workspace_bytes, void* stream);
+SMOW_API int smow_tokenizer_bwd(const float* gtokens, const void* x, const float* wa, const float* ba,
+                       const float* tokens, const float* stats,
+                       void* gx, float* gwa, float* gba, int B, int C, int64_t hw,
+                       int dtype, int layout, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

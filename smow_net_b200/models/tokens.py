@@ -111,6 +111,12 @@ class Transformer_Encoder(nn.Module):
     def forward(self, x):
         b, c, t, h, w = x.shape
         assert t == 4, "The time dimension (t) must be 4."
+        if x.is_cuda and x.dtype == torch.float32 and self.token_len == 8 and c % 4 == 0 and (c // 4) & (c // 4 - 1) == 0 \
+                and c <= 128:
+            # row N2: all four frames pooled by one hand-written pass over the stack (ops.semantic_tokens)
+            from .. import ops
+            tok = ops.semantic_tokens(x, self.conv_a.weight, self.conv_a.bias) + self.pos_embedding.unsqueeze(0)
+            return self.transformer(tok.permute(0, 2, 1, 3).reshape(b, self.token_len, t * c))
         per_frame = []
         for k in range(t):
             frame = x[:, :, k]

@@ -379,3 +379,66 @@ def tlerp_pair_cat(dec, x_t1, x_t2):
     if x_t1.shape[0] == 0:
         return tlerp_cat(dec, torch.stack((x_t1, x_t2), 2))
     return _TLerpPairCat.apply(dec, x_t1, x_t2)
+
+
+# ----------------------------------------------------------------------------- N2: semantic tokenizer
+def tokenizer_fwd_bytes(B, C, hw, s=4):
+    """Algorithmic bytes: the stack is read once (4 frames), tokens written."""
+    return B * 4 * (C * hw * s + 8 * C * 4)
+
+
+def tokenizer_bwd_bytes(B, C, hw, s=4):
+    """The stack is read once and its gradient written once."""
+    return B * 4 * (2 * C * hw * s + 2 * 8 * C * 4)
+
+
+class _SemanticTokens(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        B, C, T, H, W = x.shape
+        x = x.contiguous(memory_format=torch.channels_last_3d)
+        wa = weight.reshape(weight.shape[0], C).contiguous().float()
+        ba = bias.contiguous().float()
+        tokens = torch.empty((B, T, 8, C), dtype=torch.float32, device=x.device)
+        stats = torch.empty((B, T, 16), dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        n = int(lib.smow_tokenizer_workspace_bytes(B, C, H * W))
+        ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device_of(x):
+            _call("tokenizer_fwd", tokenizer_fwd_bytes(B, C, H * W), lib.smow_tokenizer_fwd,
+                  x.data_ptr(), wa.data_ptr(), ba.data_ptr(), tokens.data_ptr(), stats.data_ptr(), B, C, H * W,
+                  _lib.F32, _lib.NDHWC, ws.data_ptr(), n, _stream())
+        ctx.save_for_backward(x, wa, ba, tokens, stats)
+        ctx.wshape = tuple(weight.shape)
+        return tokens
+
+    @staticmethod
+    def backward(ctx, gtokens):
+        x, wa, ba, tokens, stats = ctx.saved_tensors
+        B, C, T, H, W = x.shape
+        gtokens = gtokens.contiguous().float()
+        gx = torch.empty_like(x, memory_format=torch.channels_last_3d)
+        gwa, gba = torch.empty_like(wa), torch.empty_like(ba)
+        lib = _lib.load()
+        n = int(lib.smow_tokenizer_workspace_bytes(B, C, H * W))
+        ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device_of(x):
+            _call("tokenizer_bwd", tokenizer_bwd_bytes(B, C, H * W), lib.smow_tokenizer_bwd,
+                  gtokens.data_ptr(), x.data_ptr(), wa.data_ptr(), ba.data_ptr(), tokens.data_ptr(), stats.data_ptr(),
+                  gx.data_ptr(), gwa.data_ptr(), gba.data_ptr(), B, C, H * W, _lib.F32, _lib.NDHWC,
+                  ws.data_ptr(), n, _stream())
+        return gx, gwa.view(ctx.wshape), gba
+
+
+def semantic_tokens(x, weight, bias):
+    """Spatial-attention pooling of every frame of the (B,C,4,H,W) stack to 8 tokens:
+    ``einsum('bln,bcn->blc', softmax(conv1x1(x_k)), x_k)`` for k = 0..3 (reference models/SMOW_Net.py:176-187) in one
+    pass -> (B, 4, 8, C).  ``weight`` / ``bias`` are ``conv_a``'s (8,C,1,1) and (8,)."""
+    _require_cuda(x, weight, bias)
+    if x.dim() != 5 or x.shape[2] != 4:
+        raise RuntimeError("semantic_tokens: x must be the 4-frame stack (B,C,4,H,W), got %s" % (tuple(x.shape),))
+    if weight.shape[0] != 8 or weight.shape[1] != x.shape[1] or x.dtype != torch.float32:
+        raise RuntimeError("semantic_tokens: built for token_len = 8 and fp32 stacks")
+    if x.shape[0] == 0:
+        return x.new_zeros((0, 4, 8, x.shape[1])) + 0 * (x.sum() + weight.sum() + bias.sum())
+    return _SemanticTokens.apply(x, weight, bias)

@@ -384,3 +384,59 @@ def test_tlerp_ndhwc_against_same_device_reference(case, dtype):
     cat2.backward(gcat)
     assert torch.equal(cat2.detach(), cat.detach())
     assert torch.equal(a.grad, s1.grad[:, :, 0]) and torch.equal(b.grad, s1.grad[:, :, 1])
+
+
+# ---------------------------------------------------------------------------------- N2: semantic tokenizer
+def _ref_tokens(x, weight, bias):
+    """The reference's own op sequence (models/SMOW_Net.py:176-187) per frame."""
+    b, c, t, h, w = x.shape
+    out = []
+    for k in range(t):
+        frame = x[:, :, k]
+        attn = torch.softmax(torch.nn.functional.conv2d(frame, weight, bias).reshape(b, 8, -1), dim=-1)
+        out.append(torch.einsum("bln,bcn->blc", attn, frame.reshape(b, c, -1)))
+    return torch.stack(out, 1)
+
+
+@pytest.mark.parametrize("case", [(2, 16, 128, 128, 1.0), (3, 32, 128, 128, 0.5), (1, 64, 17, 23, 2.0), (2, 4, 40, 40, 3.0),
+                                  (1, 128, 8, 8, 1.0), (2, 8, 96, 64, 0.1)])
+def test_semantic_tokens_against_reference_sequence(case):
+    B, C, H, W, wscale = case
+    g = torch.Generator(device=DEV).manual_seed(B * C + H)
+    x = torch.randn(B, C, 4, H, W, device=DEV, generator=g).contiguous(memory_format=CL3)
+    weight = torch.randn(8, C, 1, 1, device=DEV, generator=g) * wscale / C ** 0.5
+    bias = torch.randn(8, device=DEV, generator=g)
+    gt = torch.randn(B, 4, 8, C, device=DEV, generator=g)
+    leaves = [t.clone().requires_grad_(True) for t in (x, weight, bias)]
+    before = _lib.launch_count()
+    tok = ops.semantic_tokens(*leaves)
+    tok.backward(gt)
+    assert _lib.launch_count() - before == 4
+    ref_leaves = [t.double().requires_grad_(True) for t in (x, weight, bias)]
+    ref = _ref_tokens(*ref_leaves)
+    ref.backward(gt.double())
+    assert float((tok.detach() - ref.detach()).abs().max()) <= 1e-5
+    for name, a, b in zip(("gx", "gweight", "gbias"), leaves, ref_leaves):
+        err = float((a.grad.double() - b.grad).abs().max())
+        assert err <= 1e-5 * max(1.0, float(b.grad.abs().max())), (name, err)
+    assert leaves[0].grad.is_contiguous(memory_format=CL3)
+    # fixed summation order: bit-reproducible
+    leaves2 = [t.clone().requires_grad_(True) for t in (x, weight, bias)]
+    tok2 = ops.semantic_tokens(*leaves2)
+    tok2.backward(gt)
+    assert torch.equal(tok2, tok) and all(torch.equal(a.grad, b.grad) for a, b in zip(leaves, leaves2))
+
+
+def test_semantic_tokens_sharp_attention_and_errors():
+    """Large logits (one-hot attention) stay finite; unsupported inputs raise instead of falling back."""
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x = torch.randn(1, 16, 4, 64, 64, device=DEV, generator=g).contiguous(memory_format=CL3) * 30
+    weight = torch.randn(8, 16, 1, 1, device=DEV, generator=g)
+    bias = torch.zeros(8, device=DEV)
+    tok = ops.semantic_tokens(x, weight, bias)
+    ref = _ref_tokens(x.double(), weight.double(), bias.double())
+    assert bool(torch.isfinite(tok).all()) and float((tok - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+    with pytest.raises(RuntimeError):
+        ops.semantic_tokens(x.cpu(), weight.cpu(), bias.cpu())
+    with pytest.raises(RuntimeError):
+        ops.semantic_tokens(x[:, :12], weight[:, :12], bias)      # C/4 = 3 is not a power of two
