@@ -43,6 +43,11 @@ def main():
             cat = ops.tlerp_cat(dec, x)
             cat.backward(torch.cat([gout, gout], 1).contiguous(memory_format=torch.channels_last_3d if a.layout == 'ndhwc' else torch.contiguous_format))
             x.grad = None
+            if a.layout == "ndhwc" and dt == torch.float32:
+                w = (torch.randn(8, a.C, 1, 1, device=dev, generator=g) / a.C ** 0.5).requires_grad_(True)
+                bias = torch.zeros(8, device=dev, requires_grad=True)
+                stack = dec.detach().requires_grad_(True)
+                ops.semantic_tokens(stack, w, bias).backward(torch.randn(a.B, 4, 8, a.C, device=dev, generator=g))
             torch.cuda.synchronize()
         print(i, {k: "%.3f ms %.0f GB/s" % (v["ms"], v["gbps"]) for k, v in kt.summary().items()})
 

@@ -109,14 +109,14 @@ def kernels(tag):
         f.write("# %s — `ncu --set full --clock-control none` of the hand-written kernels\n\n" % tag)
         f.write("Raw reports stay in gpurun_out/ (scratch); this file is the committed summary. Durations under ncu are\n"
                 "cold-cache and serialised; CUDA-event timings are in the sweep / bench files.\n")
-        for part, title in (("cold", "HBM-cold: benchmarks/one_kernel.py --C 32 --H 128 --B 64 (fp32, 1.07 GB working set)"),
+        for part, title in (("cold", "HBM-cold: benchmarks/one_kernel.py --C 32 --H 128 --B 64 --layout ndhwc (fp32, 1.07 GB working set)"),
                             ("instep", "inside one bench step (SMOW_Net_LW, batch 16; operands partly L2-resident)")):
             rep = os.path.join(OUT, "%s_%s_kernels.ncu-rep" % (tag, part))
             if not os.path.exists(rep):
                 continue
             rows = ncu_raw(rep)
             f.write("\n## %s\n\n| # | kernel | %s |\n|---|---|%s\n" % (title, " | ".join(t for _, t in METRICS), "---:|" * len(METRICS)))
-            rows = [d for d in rows if d["name"].startswith(("warp_", "tlerp_"))]
+            rows = [d for d in rows if d["name"].startswith(("warp_", "tlerp_", "tok_"))]
             for i, d in enumerate(rows):
                 cells = []
                 for m, _ in METRICS:
@@ -134,22 +134,27 @@ def kernels(tag):
                 f.write("| %d | %s | %s |\n" % (i, d["name"][:60], " | ".join(cells)))
                 if part == "instep":
                     key = re.sub(r"<.*", "", d["name"])
-                    t = traffic.setdefault(key, [0, 0.0])
+                    t = traffic.setdefault(key, [0, 0.0, 0.0])
+                    b = d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
                     t[0] += 1
-                    t[1] += d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
+                    t[1] += b
+                    t[2] = max(t[2], b)
     if traffic:
         op_of = {"warp_fwd": "warp_stack_fwd", "warp_stack_fwd": "warp_stack_fwd", "warp_bwd": "warp_stack_bwd",
-                 "warp_stack_bwd": "warp_stack_bwd", "tlerp_cat_fwd": "tlerp_cat_fwd", "tlerp_cat_bwd": "tlerp_cat_bwd"}
+                 "warp_stack_bwd": "warp_stack_bwd", "tlerp_cat_fwd": "tlerp_cat_fwd", "tlerp_cat_bwd": "tlerp_cat_bwd",
+                 "tok_fwd": "tokenizer_fwd", "tok_bwd": "tokenizer_bwd"}
         per_op = {}
-        for k, (n, b) in traffic.items():
+        for k, (n, b, bmax) in traffic.items():
             for pre, op in op_of.items():
                 if k.startswith(pre):
-                    o = per_op.setdefault(op, {"launches": 0, "bytes": 0.0})
-                    if "far" not in k:
+                    o = per_op.setdefault(op, {"launches": 0, "bytes": 0.0, "largest": 0.0})
+                    o["largest"] = max(o["largest"], bmax)
+                    if "far" not in k and "combine" not in k:      # side kernels of the same C-ABI call
                         o["launches"] += n
                     o["bytes"] += b
                     break
         res = {op: v["bytes"] / max(1, v["launches"]) for op, v in per_op.items()}
+        res.update({op + "@largest": v["largest"] for op, v in per_op.items()})      # the operator's biggest launch
         res["_source"] = "profiles/%s_ncu_kernels.md (in-step capture), dram__bytes_read+write per C-ABI call" % tag
         json.dump(res, open(os.path.join(PROF, "roofline_traffic.json"), "w"), indent=1)
 
@@ -164,17 +169,18 @@ def sweep(tag):
         f.write("`python benchmarks/sweep_warp.py --iters 10`; working set >= 1 GiB per launch (HBM-cold). GB/s = ALGORITHMIC bytes\n"
                 "(SURVEY §8(d)) / time; frac = of the measured copy bandwidth (MEASURED_PEAKS.json, 6547.8 GB/s); ref = the reference's\n"
                 "own op sequence (F.grid_sample + cat / F.interpolate + cat, ATen sm_100 kernels) on the same GPU.\n"
-                "variant: 0 direct / atomics, 1 bulk-copy staged planes, 2 channel-vectorised tiles, 9 NDHWC (channels_last_3d) kernels.\n\n")
+                "variant: 0 direct / atomics, 1 bulk-copy staged planes, 2 channel-vectorised tiles (NCDHW); 9 NDHWC (channels_last_3d)\n"
+                "kernels as the modules run them (backward = tile gather + far pass), 8 NDHWC vector-atomic scatter backward.\n\n")
         f.write("| op | dtype | C | H=W | B | sigma | variant | ms | GB/s | frac | ref ms | speed-up |\n|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
         for r in rows:
-            if not r["op"].startswith("warp"):
+            if not r["op"].startswith(("warp", "tokenizer")):
                 continue
             f.write("| %s | %s | %d | %d | %d | %.1f | %d | %.3f | %.0f | %.2f | %s | %s |\n" % (
                 r["op"], r["dtype"], r["C"], r["H"], r["B"], r["sigma"], r["variant"], r["ms"], r["gbps"], r["frac"],
                 "%.3f" % r["ref_ms"] if r["ref_ms"] else "-", "%.1fx" % r["speedup"] if r["speedup"] else "-"))
         f.write("\n| op | dtype | Cd | Cs | h=w | B | variant | ms | GB/s | frac | ref ms | speed-up |\n|---|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
         for r in rows:
-            if r["op"].startswith("warp"):
+            if r["op"].startswith(("warp", "tokenizer")):
                 continue
             f.write("| %s | %s | %d | %d | %d | %d | %d | %.3f | %.0f | %.2f | %.3f | %.1fx |\n" % (
                 r["op"], r["dtype"], r["Cd"], r["Cs"], r["h"], r["B"], r["variant"], r["ms"], r["gbps"], r["frac"], r["ref_ms"], r["speedup"]))

@@ -117,13 +117,54 @@ def sweep_warp(args, emit):
                     def bwdc():
                         xcg.grad = fcg.grad = None
                         outc.backward(gc, retain_graph=True)
-                    ms = time_fn(bwdc, args.warm, args.iters)
                     nb = ops.warp_bwd_bytes(B, C, H, W, s)
-                    emit(dict(base, op="warp_stack_bwd", variant=9, ms=ms, gbps=nb / ms / 1e6, frac=nb / ms / 1e6 / peak(),
-                              ref_ms=ref_b, speedup=(ref_b / ms) if ref_b else None))
+                    # variant 9 = default NDHWC backward (tile gather + far pass), 8 = vector-atomic scatter
+                    for tag, opt in ((9, -1), (8, 0)):
+                        _lib.set_option("warp_bwd_variant", opt)
+                        ms = time_fn(bwdc, args.warm, args.iters)
+                        emit(dict(base, op="warp_stack_bwd", variant=tag, ms=ms, gbps=nb / ms / 1e6,
+                                  frac=nb / ms / 1e6 / peak(), ref_ms=ref_b, speedup=(ref_b / ms) if ref_b else None))
+                    _lib.set_option("warp_bwd_variant", -1)
                     del xc, gc, xcg, fcg, outc
                 del x, flow, gout, out, xg, fg
                 torch.cuda.empty_cache()
+
+
+def sweep_tokenizer(args, emit):
+    """Row N2: semantic tokenizer vs the reference's per-frame conv + softmax + einsum sequence."""
+    dev, cl = "cuda:0", torch.channels_last_3d
+    for C, H, B in ((16, 128, 16), (16, 128, 128), (32, 128, 16), (32, 128, 64)):
+        g = torch.Generator(device=dev).manual_seed(3)
+        x = torch.randn(B, C, 4, H, H, device=dev, generator=g).contiguous(memory_format=cl).requires_grad_(True)
+        w = (torch.randn(8, C, 1, 1, device=dev, generator=g) / C ** 0.5).requires_grad_(True)
+        bias = torch.randn(8, device=dev, generator=g).requires_grad_(True)
+        gt = torch.randn(B, 4, 8, C, device=dev, generator=g)
+
+        def ref(x, w, bias):
+            out = []
+            for k in range(4):
+                f = x[:, :, k]
+                a = torch.softmax(torch.nn.functional.conv2d(f, w, bias).reshape(B, 8, -1), dim=-1)
+                out.append(torch.einsum("bln,bcn->blc", a, f.reshape(B, C, -1)))
+            return torch.stack(out, 1)
+        base = {"C": C, "H": H, "W": H, "B": B, "dtype": "float32", "sigma": 0.0}
+        res = {}
+        for name, fn in (("ref", ref), ("ours", ops.semantic_tokens)):
+            with torch.no_grad():
+                f = time_fn(lambda: fn(x, w, bias), args.warm, args.iters)
+            tok = fn(x, w, bias)
+
+            def bwd():
+                x.grad = w.grad = bias.grad = None
+                tok.backward(gt, retain_graph=True)
+            res[name] = (f, time_fn(bwd, args.warm, args.iters))
+        for i, (op, nb) in enumerate((("tokenizer_fwd", ops.tokenizer_fwd_bytes(B, C, H * H)),
+                                      ("tokenizer_bwd", ops.tokenizer_bwd_bytes(B, C, H * H)))):
+            ms, rms = res["ours"][i], res["ref"][i]
+            emit(dict(base, op=op, variant=9, ms=ms, gbps=nb / ms / 1e6, frac=nb / ms / 1e6 / peak(), ref_ms=rms,
+                      speedup=rms / ms))
+        del x, tok
+        torch.cuda.empty_cache()
 
 
 def sweep_tlerp(args, emit):
@@ -192,7 +233,7 @@ def sweep_tlerp(args, emit):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default="", choices=["", "warp", "tlerp"])
+    ap.add_argument("--only", default="", choices=["", "warp", "tlerp", "tokenizer"])
     ap.add_argument("--min-bytes", type=int, default=1 << 30)
     ap.add_argument("--warm", type=int, default=5)
     ap.add_argument("--iters", type=int, default=20)
@@ -213,6 +254,8 @@ def main():
         sweep_warp(args, emit)
     if args.only in ("", "tlerp"):
         sweep_tlerp(args, emit)
+    if args.only in ("", "tokenizer"):
+        sweep_tokenizer(args, emit)
     for k, v in saved.items():
         _lib.set_option(k, v)
 

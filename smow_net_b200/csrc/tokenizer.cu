@@ -223,25 +223,40 @@ tok_fwd_chunk_kernel(const float* __restrict__ x, const float* __restrict__ wa, 
 }
 
 // ---- forward, pass 2: combine the chunks of one (pair, frame) -------------------------------------------------------
-// grid 4*B, threads = L*C rounded up to 32.  tokens: [bk][L][C]; stats: [bk][ M[8] | 1/S[8] ]
-__global__ void tok_fwd_combine_kernel(const float* __restrict__ part, float* __restrict__ tokens,
-                                       float* __restrict__ stats, TokGeom g) {
-  const int C = g.C, bk = blockIdx.x;
+// One warp per (pair-frame, token): lanes run over the chunks, every reduction is a fixed-order butterfly.
+// grid = ceil(4*B*8 / 8) CTAs of 8 warps.  tokens: [bk][L][C]; stats: [bk][ M[8] | 1/S[8] ]
+__global__ void __launch_bounds__(256)
+tok_fwd_combine_kernel(const float* __restrict__ part, float* __restrict__ tokens, float* __restrict__ stats,
+                       TokGeom g, int n_bk) {
+  const int C = g.C, lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * 8 + (threadIdx.x >> 5);            // = bk * 8 + l
+  if (wid >= n_bk * TOK_L) return;
+  const int bk = wid >> 3, l = wid & 7;
   const int stride = 2 * TOK_L + TOK_L * C;
   const float* pb = part + (int64_t)bk * g.nchunks * stride;
-  for (int i = threadIdx.x; i < TOK_L * C; i += blockDim.x) {
-    const int l = i / C;
-    float M = -INFINITY;
-    for (int k = 0; k < g.nchunks; ++k) M = fmaxf(M, pb[k * stride + l]);
-    float S = 0.f, T = 0.f;
-    for (int k = 0; k < g.nchunks; ++k) {
+  float M = -INFINITY;
+  for (int k = lane; k < g.nchunks; k += 32) M = fmaxf(M, pb[k * stride + l]);
+  for (int d = 16; d > 0; d >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, d));
+  float S = 0.f;
+  for (int k = lane; k < g.nchunks; k += 32) S = fmaf(pb[k * stride + TOK_L + l], expf(pb[k * stride + l] - M), S);
+  for (int d = 16; d > 0; d >>= 1) S += __shfl_xor_sync(0xffffffffu, S, d);
+  const float rS = __fdiv_rn(1.f, S);
+  for (int c0 = 0; c0 < C; c0 += 4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = lane; k < g.nchunks; k += 32) {
       const float sc = expf(pb[k * stride + l] - M);
-      S = fmaf(pb[k * stride + TOK_L + l], sc, S);
-      T = fmaf(pb[k * stride + 2 * TOK_L + i], sc, T);
+      const float4 v = *reinterpret_cast<const float4*>(pb + k * stride + 2 * TOK_L + l * C + c0);
+      t.x = fmaf(v.x, sc, t.x); t.y = fmaf(v.y, sc, t.y); t.z = fmaf(v.z, sc, t.z); t.w = fmaf(v.w, sc, t.w);
     }
-    tokens[(int64_t)bk * TOK_L * C + i] = __fdiv_rn(T, S);
-    if (i == l * C) { stats[bk * 2 * TOK_L + l] = M; stats[bk * 2 * TOK_L + TOK_L + l] = __fdiv_rn(1.f, S); }
+    for (int d = 16; d > 0; d >>= 1) {
+      t.x += __shfl_xor_sync(0xffffffffu, t.x, d); t.y += __shfl_xor_sync(0xffffffffu, t.y, d);
+      t.z += __shfl_xor_sync(0xffffffffu, t.z, d); t.w += __shfl_xor_sync(0xffffffffu, t.w, d);
+    }
+    if (lane == 0)
+      *reinterpret_cast<float4*>(tokens + (int64_t)bk * TOK_L * C + l * C + c0) =
+          make_float4(__fmul_rn(t.x, rS), __fmul_rn(t.y, rS), __fmul_rn(t.z, rS), __fmul_rn(t.w, rS));
   }
+  if (lane == 0) { stats[bk * 2 * TOK_L + l] = M; stats[bk * 2 * TOK_L + TOK_L + l] = rS; }
 }
 
 // ---- backward: one pass ---------------------------------------------------------------------------------------------
@@ -356,14 +371,23 @@ tok_bwd_chunk_kernel(const float* __restrict__ gtok, const float* __restrict__ x
   reduce_tiles<CG, NT>(dw, db, accs, out, out + TOK_L * C, C, LP);
 }
 
-// gwa[L][C], gba[L] = sum over every (pair, frame, chunk) partial, in index order.  grid = ceil((L*C + L) / 128)
-__global__ void tok_bwd_combine_kernel(const float* __restrict__ part, float* __restrict__ gwa, float* __restrict__ gba,
-                                       int n_part, int C) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, n = TOK_L * C + TOK_L;
-  if (i >= n) return;
+// gwa[L][C], gba[L] = sum over every (pair, frame, chunk) partial.  One CTA per output element: 256 threads stride over
+// the partials, then a fixed-order butterfly + 8-warp sum (deterministic).  grid = L*C + L
+__global__ void __launch_bounds__(256)
+tok_bwd_combine_kernel(const float* __restrict__ part, float* __restrict__ gwa, float* __restrict__ gba, int n_part,
+                       int C) {
+  __shared__ float red[8];
+  const int i = blockIdx.x, n = TOK_L * C + TOK_L;
   float t = 0.f;
-  for (int k = 0; k < n_part; ++k) t += part[(int64_t)k * n + i];
-  if (i < TOK_L * C) gwa[i] = t; else gba[i - TOK_L * C] = t;
+  for (int k = threadIdx.x; k < n_part; k += 256) t += part[(int64_t)k * n + i];
+  for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    for (int wv = 0; wv < 8; ++wv) r += red[wv];
+    if (i < TOK_L * C) gwa[i] = r; else gba[i - TOK_L * C] = r;
+  }
 }
 
 static int tok_geom(TokGeom& g, int B, int C, int64_t hw, const void* x, int dtype, int layout) {
@@ -422,8 +446,7 @@ int smow_tokenizer_fwd(const void* x, const float* wa, const float* ba, float* t
     default: if (g.G == 1) { SMOW_TOK_FWD(16, 8); } else { SMOW_TOK_FWD(16, 16); } break;
   }
 #undef SMOW_TOK_FWD
-  int th = TOK_L * C; th = th > 256 ? 256 : ((th + 31) / 32) * 32;
-  tok_fwd_combine_kernel<<<4 * B, th, 0, st>>>(part, tokens, stats, g);
+  tok_fwd_combine_kernel<<<(4 * B * TOK_L + 7) / 8, 256, 0, st>>>(part, tokens, stats, g, 4 * B);
   count_launch(2);
   return check_launch("tokenizer_fwd");
 }
@@ -449,8 +472,7 @@ int smow_tokenizer_bwd(const float* gtokens, const void* x, const float* wa, con
     default: SMOW_TOK_BWD(16); break;
   }
 #undef SMOW_TOK_BWD
-  const int n = TOK_L * C + TOK_L;
-  tok_bwd_combine_kernel<<<(n + 127) / 128, 128, 0, st>>>(part, gwa, gba, 4 * B * g.nchunks, C);
+  tok_bwd_combine_kernel<<<TOK_L * C + TOK_L, 256, 0, st>>>(part, gwa, gba, 4 * B * g.nchunks, C);
   count_launch(2);
   return check_launch("tokenizer_bwd");
 }

@@ -93,11 +93,12 @@ class KernelTimer:
     def __init__(self):
         self.records = []  # (name, algorithmic_bytes, start_event, end_event)
 
-    def summary(self):
+    def summary(self, by_shape=False):
+        """Per operator totals; by_shape=True keeps launches of different sizes apart (key 'name@<bytes>')."""
         out = {}
         for name, nbytes, e0, e1 in self.records:
             ms = e0.elapsed_time(e1)
-            s = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0})
+            s = out.setdefault("%s@%d" % (name, nbytes) if by_shape else name, {"calls": 0, "ms": 0.0, "bytes": 0})
             s["calls"] += 1
             s["ms"] += ms
             s["bytes"] += nbytes
