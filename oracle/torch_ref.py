@@ -60,3 +60,16 @@ def tlerp_cat_with_grads(dec, skip, gcat):
     cat = ref_tlerp_cat(d, skip)
     cat.backward(gcat)
     return cat.detach(), (None if d is None else d.grad.detach()), skip.grad.detach()
+
+
+def ref_semantic_tokens(x, weight, bias):
+    """The reference's tokenizer loop (models/SMOW_Net.py:176-187 = models/SMOW_Net_LW.py:195-206), per frame:
+    conv_a (1x1, C -> 8) -> view(b, 8, H*W) -> softmax(dim=-1) -> einsum('bln,bcn->blc').  Returns (B, 4, 8, C);
+    the positional embedding and the concat of the four token sets are left to the caller."""
+    b, c, t, h, w = x.shape
+    out = []
+    for k in range(t):
+        frame = x[:, :, k]
+        attn = torch.softmax(F.conv2d(frame, weight, bias).reshape(b, weight.shape[0], -1), dim=-1)
+        out.append(torch.einsum("bln,bcn->blc", attn, frame.reshape(b, c, -1)))
+    return torch.stack(out, 1)

@@ -387,15 +387,7 @@ def test_tlerp_ndhwc_against_same_device_reference(case, dtype):
 
 
 # ---------------------------------------------------------------------------------- N2: semantic tokenizer
-def _ref_tokens(x, weight, bias):
-    """The reference's own op sequence (models/SMOW_Net.py:176-187) per frame."""
-    b, c, t, h, w = x.shape
-    out = []
-    for k in range(t):
-        frame = x[:, :, k]
-        attn = torch.softmax(torch.nn.functional.conv2d(frame, weight, bias).reshape(b, 8, -1), dim=-1)
-        out.append(torch.einsum("bln,bcn->blc", attn, frame.reshape(b, c, -1)))
-    return torch.stack(out, 1)
+_ref_tokens = torch_ref.ref_semantic_tokens      # the reference's own op sequence (models/SMOW_Net.py:176-187)
 
 
 @pytest.mark.parametrize("case", [(2, 16, 128, 128, 1.0), (3, 32, 128, 128, 0.5), (1, 64, 17, 23, 2.0), (2, 4, 40, 40, 3.0),
