@@ -43,6 +43,23 @@ __device__ __forceinline__ void split_index(int64_t i, int64_t per_row, bool sma
   }
 }
 
+// exact division of a dividend < 2^31 by a runtime constant: q = (n * m) >> sh, m = floor(2^sh / d) + 1,
+// sh = 31 + ceil(log2 d)  (error term n*e / (d * 2^sh) < 1/d).  Three instructions instead of ~20.
+struct FastDiv { uint32_t d, m; int sh; };
+static FastDiv make_fastdiv(int64_t d64) {
+  FastDiv f;
+  f.d = (uint32_t)d64;
+  int L = 0;
+  while ((1ull << L) < (uint64_t)d64) ++L;
+  f.sh = 31 + L;
+  f.m = (uint32_t)(((1ull << f.sh) / (uint64_t)d64) + 1ull);
+  return f;
+}
+__device__ __forceinline__ void fast_split(uint32_t i, const FastDiv& f, uint32_t& row, uint32_t& col) {
+  row = (uint32_t)(((uint64_t)i * f.m) >> f.sh);
+  col = i - row * f.d;
+}
+
 struct LerpW { float a1, b1, a2, b2; };
 __device__ __forceinline__ LerpW lerp_weights() {
   LerpW w;
@@ -155,12 +172,40 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, const T* __restrict__ s2,
                            int64_t sB, T* __restrict__ cat, int Cd, int Cs, int64_t hw, int64_t n_items,
-                           bool do_copy, bool do_lerp) {
+                           bool do_copy, bool do_lerp, FastDiv fqt, FastDiv fhw) {
   constexpr int V = Vec<T>::N;
   const int Ct = Cd + Cs;
   const int64_t qd = Cd / V, qt = Ct / V;
   const LerpW lw = lerp_weights();
   const bool small = n_items < (1ll << 31);
+  if (small) {          // every index fits 32 bits: multiply-shift divisions, 32-bit offsets (the models' shapes)
+    const uint32_t n32 = (uint32_t)n_items, step = gridDim.x * 256u, uqd = (uint32_t)qd;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n32; i += step) {
+      uint32_t r, vt;
+      fast_split(i, fqt, r, vt);               // r = (b*4 + slot)*hw + p
+      T* dst = cat + ((int64_t)i * V);         // = cat + r*Ct + vt*V: the output is written densely
+      if (vt < uqd) {
+        if (do_copy) stv(dst, ldv_stream(dec + ((int64_t)r * Cd + vt * V)));
+        continue;
+      }
+      if (!do_lerp) continue;
+      uint32_t bs, p;
+      fast_split(r, fhw, bs, p);
+      const uint32_t slot = bs & 3u;
+      const int64_t off = (int64_t)(bs >> 2) * sB + (int64_t)(p * (uint32_t)Cs + (vt - uqd) * V);
+      Vec<T> o;
+      if (slot == 0) o = ldv(s1 + off);
+      else if (slot == 3) o = ldv(s2 + off);
+      else {
+        const Vec<T> a = ldv(s1 + off), bb = ldv(s2 + off);
+        const float wa = slot == 1 ? lw.a1 : lw.a2, wb = slot == 1 ? lw.b1 : lw.b2;
+#pragma unroll
+        for (int j = 0; j < V; ++j) o.v[j] = fromf<T>(fmaf(wa, cvtf<T>(a.v[j]), __fmul_rn(wb, cvtf<T>(bb.v[j]))));
+      }
+      stv(dst, o);
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_items; i += (int64_t)gridDim.x * 256) {
     int64_t r, vt;
     split_index(i, qt, small, r, vt);          // r = (b*4 + slot)*hw + p
@@ -190,16 +235,23 @@ tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 tlerp_cat_bwd_ndhwc_kernel(const T* __restrict__ gcat, T* __restrict__ g1, T* __restrict__ g2, int64_t sB, int Cd,
-                           int Cs, int64_t hw, int64_t n) {
+                           int Cs, int64_t hw, int64_t n, FastDiv fqs, FastDiv fhw) {
   constexpr int V = Vec<T>::N;
   const int Ct = Cd + Cs;
   const LerpW lw = lerp_weights();
   const int64_t qs = Cs / V, fs = hw * Ct;
-  const bool small = n < (1ll << 31);
+  const bool small = n < (1ll << 31) && (int64_t)4 * hw * Ct < (1ll << 31);
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     int64_t bp, vs, b, p;
-    split_index(i, qs, small, bp, vs);
-    split_index(bp, hw, small, b, p);
+    if (small) {
+      uint32_t ubp, uvs, ub, up;
+      fast_split((uint32_t)i, fqs, ubp, uvs);
+      fast_split(ubp, fhw, ub, up);
+      bp = ubp; vs = uvs; b = ub; p = up;
+    } else {
+      split_index(i, qs, false, bp, vs);
+      split_index(bp, hw, false, b, p);
+    }
     const T* g = gcat + ((b * 4) * hw + p) * Ct + Cd + vs * V;
     const Vec<T> a = ldv_stream(g), m1 = ldv_stream(g + fs), m2 = ldv_stream(g + 2 * fs), d = ldv_stream(g + 3 * fs);
     Vec<T> r1, r2;
@@ -268,7 +320,8 @@ static int fwd_ndhwc(const T* dec, const T* s1, const T* s2, int64_t sB, T* cat,
   const int64_t n_items = (int64_t)B * 4 * hw * ((Cd + Cs) / V);
   const int cap = device_info().sms * 8;
   const int nb = (int)((n_items + 255) / 256 < cap ? (n_items + 255) / 256 : cap);
-  tlerp_cat_fwd_ndhwc_kernel<T><<<nb, 256, 0, st>>>(dec, s1, s2, sB, cat, Cd, Cs, hw, n_items, do_copy, do_lerp);
+  tlerp_cat_fwd_ndhwc_kernel<T><<<nb, 256, 0, st>>>(dec, s1, s2, sB, cat, Cd, Cs, hw, n_items, do_copy, do_lerp,
+                                                    make_fastdiv((Cd + Cs) / V), make_fastdiv(hw));
   count_launch();
   return check_launch("tlerp_cat_fwd (NDHWC)");
 }
@@ -281,7 +334,7 @@ static int bwd_ndhwc(const T* gcat, T* g1, T* g2, int64_t sB, int B, int Cd, int
   const int64_t n = (int64_t)B * hw * (Cs / V);
   const int cap = device_info().sms * 8;
   const int nb = (int)((n + 255) / 256 < cap ? (n + 255) / 256 : cap);
-  tlerp_cat_bwd_ndhwc_kernel<T><<<nb, 256, 0, st>>>(gcat, g1, g2, sB, Cd, Cs, hw, n);
+  tlerp_cat_bwd_ndhwc_kernel<T><<<nb, 256, 0, st>>>(gcat, g1, g2, sB, Cd, Cs, hw, n, make_fastdiv(Cs / V), make_fastdiv(hw));
   count_launch();
   return check_launch("tlerp_cat_bwd (NDHWC)");
 }
