@@ -104,6 +104,77 @@ warp_fwd_ndhwc_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int64_
       __ldg(reinterpret_cast<const uint4*>(src + (int64_t)p * C));    // un-warped slot: bit-exact copy
 }
 
+// Same forward with the coordinate chain de-duplicated across the lanes of a pixel (q = C/V a power of two <= 32):
+// a warp owns 32 consecutive pixels.  Lane l runs the reference's coordinate chain for pixel l ONCE (~100 instructions
+// per 32 pixels instead of per (pixel, vector)); then, in q steps of 32/q pixels, every lane fetches the footprint of
+// the pixel it serves with indexed shuffles and does only the gather / FMA / store work.  Arithmetic and rounding are
+// unchanged (bit-identical results); 3.5x fewer instructions at C = 32.
+// grid: x = ceil(HW / 256) (8 warps x 32 pixels), y = 2*B.
+template <typename T>
+__global__ void __launch_bounds__(256)
+warp_fwd_ndhwc_shfl_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int64_t sB,
+                           const float* __restrict__ flow, const float* __restrict__ xs, const float* __restrict__ ys,
+                           T* __restrict__ out, int C, int H, int W, int q, int qshift, int wshift) {
+  constexpr int V = CVec<T>::N;
+  const int HW = H * W;
+  const int lane = threadIdx.x & 31;
+  const int pbase = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+  if (pbase >= HW) return;                                       // warp-uniform
+  const int b = blockIdx.y >> 1, t = blockIdx.y & 1;
+  // ---- one coordinate chain per pixel ----
+  int own_o = 0, own_flags = 0;
+  float own_nw = 0.f, own_ne = 0.f, own_sw = 0.f, own_se = 0.f;
+  {
+    const int p = pbase + lane;
+    if (p < HW) {
+      const int h = wshift >= 0 ? (p >> wshift) : (p / W), w = p - h * W;
+      const int64_t fo = ((int64_t)(b * 2) * 2 + t) * HW + p;
+      const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
+      own_nw = __fmul_rn(fp.wx0, fp.wy0); own_ne = __fmul_rn(fp.wx1, fp.wy0);
+      own_sw = __fmul_rn(fp.wx0, fp.wy1); own_se = __fmul_rn(fp.wx1, fp.wy1);
+      own_o = fp.y0 * W + fp.x0;
+      own_flags = (fp.x1ok ? 1 : 0) | (fp.y1ok ? 2 : 0);
+    }
+  }
+  // ---- q steps: lanes = (32/q pixels) x (q channel vectors) ----
+  const int v = lane & (q - 1), sub = lane >> qshift, ppw = 32 >> qshift;
+  const T* src = (t ? x2 : x1) + b * sB + v * V;
+  T* ob = out + (int64_t)b * 4 * HW * C + v * V;
+  const int64_t slotC = (int64_t)HW * C;
+  for (int j = 0; j < q; ++j) {
+    const int sl = j * ppw + sub;                                 // lane that holds this pixel's footprint
+    const int o_nw = __shfl_sync(0xffffffffu, own_o, sl), flags = __shfl_sync(0xffffffffu, own_flags, sl);
+    const float nw = __shfl_sync(0xffffffffu, own_nw, sl), ne = __shfl_sync(0xffffffffu, own_ne, sl);
+    const float sw = __shfl_sync(0xffffffffu, own_sw, sl), se = __shfl_sync(0xffffffffu, own_se, sl);
+    const int p = pbase + sl;
+    if (p >= HW) continue;
+    const T* tp = src + (int64_t)o_nw * C;
+    const Pack<T> a = ld_pack<T>(tp);
+    const uint4 pass = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)p * C));
+    Pack<T> r;
+#pragma unroll
+    for (int k = 0; k < V; ++k) r.f[k] = __fmul_rn(a.f[k], nw);        // ATen order nw, ne, sw, se; skip OOB taps
+    if (flags & 1) {
+      const Pack<T> c = ld_pack<T>(tp + C);
+#pragma unroll
+      for (int k = 0; k < V; ++k) r.f[k] = fmaf(c.f[k], ne, r.f[k]);
+    }
+    if (flags & 2) {
+      const Pack<T> c = ld_pack<T>(tp + (int64_t)W * C);
+#pragma unroll
+      for (int k = 0; k < V; ++k) r.f[k] = fmaf(c.f[k], sw, r.f[k]);
+    }
+    if (flags == 3) {
+      const Pack<T> c = ld_pack<T>(tp + (int64_t)(W + 1) * C);
+#pragma unroll
+      for (int k = 0; k < V; ++k) r.f[k] = fmaf(c.f[k], se, r.f[k]);
+    }
+    T* o = ob + (int64_t)p * C;
+    st_pack<T>(o + (1 + t) * slotC, r);
+    *reinterpret_cast<uint4*>(o + (t ? 3 : 0) * slotC) = pass;            // un-warped slot: bit-exact copy
+  }
+}
+
 // ------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------
@@ -661,8 +732,14 @@ int warp_fwd_ndhwc(const T* x1, const T* x2, int64_t sB, const float* flow, cons
     return fail(SMOW_EALIGN, "NDHWC warp needs C %% %d == 0 and 16 B aligned tensors", V);
   const int q = C / V;
   if ((int64_t)H * W * q >= (1ll << 31)) return fail(SMOW_ERANGE, "plane too large");
-  dim3 grid((unsigned)(((int64_t)H * W * q + 255) / 256), 2 * B);
-  warp_fwd_ndhwc_kernel<T><<<grid, 256, 0, st>>>(x1, x2, sB, flow, xs, ys, out, C, H, W, q, ilog2_exact(q));
+  const int qs = ilog2_exact(q);
+  if (qs >= 0 && q <= 32 && option(OPT_WARP_FWD_VARIANT) != 0) {          // default: per-pixel coordinates, shuffled
+    dim3 grid((unsigned)(((int64_t)H * W + 255) / 256), 2 * B);
+    warp_fwd_ndhwc_shfl_kernel<T><<<grid, 256, 0, st>>>(x1, x2, sB, flow, xs, ys, out, C, H, W, q, qs, ilog2_exact(W));
+  } else {                                                                 // any q; also warp_fwd_variant = 0
+    dim3 grid((unsigned)(((int64_t)H * W * q + 255) / 256), 2 * B);
+    warp_fwd_ndhwc_kernel<T><<<grid, 256, 0, st>>>(x1, x2, sB, flow, xs, ys, out, C, H, W, q, qs);
+  }
   count_launch();
   return check_launch("warp_fwd_ndhwc");
 }
