@@ -80,27 +80,43 @@ def train(args):
     rank, local_rank, world, device = init_distributed()
     synthetic.seed_everything(2022, rank)
     lo, hi = synthetic.shard_range(args.global_batch, rank, world)
-    model = wrap_ddp(build_model(args.model, device), device, world).train()
-    opt = S.make_optimizer(model)
+    graphed = getattr(args, "graph", False) and device.type == "cuda"
+    if graphed and world > 1:
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):                      # DDP must be built off the default stream to be captured
+            model = wrap_ddp(build_model(args.model, device), device, world).train()
+        torch.cuda.current_stream().wait_stream(side)
+    else:
+        model = wrap_ddp(build_model(args.model, device), device, world).train()
+    opt = S.make_optimizer(model, capturable=graphed)
     sched = S.make_scheduler(opt, args.steps + args.warmup)
     a, b, y = synthetic.make_batch(hi - lo, device=device, seed=2022 + rank)
+    step = lambda: S.train_step(model, opt, sched, a, b, y)
+    if graphed:       # forward + loss + backward (+ all-reduce) + clip + AdamW in ONE CUDA graph; the LR schedule steps outside
+        from . import graph as G
+        gs = G.GraphedStep(model, a, b, y, optimizer=opt, scheduler=sched, warmup=11 if world > 1 else 3)
+        step = lambda: gs()
     for _ in range(args.warmup):
-        S.train_step(model, opt, sched, a, b, y)
+        step()
     if device.type == "cuda":
         torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        loss = S.train_step(model, opt, sched, a, b, y)
+        loss = step()
     if device.type == "cuda":
         torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0, device, world)
     if rank == 0:
         print(json.dumps({"mode": "train", "model": args.model, "n_gpus": world, "global_batch": args.global_batch,
                           "steps": args.steps, "ms_per_step": 1e3 * dt / max(1, args.steps),
-                          "pairs_per_s": args.global_batch * args.steps / dt, "loss": float(loss)}))
+                          "pairs_per_s": args.global_batch * args.steps / dt, "loss": float(loss.detach()),
+                          "launch": "cuda-graph" if graphed else "eager"}), flush=True)
     if world > 1:
+        if graphed:       # a captured graph keeps NCCL work alive; ProcessGroupNCCL's teardown would wait for ever
+            dist.barrier()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -146,6 +162,7 @@ def main(argv=None):
     t.add_argument("--global-batch", type=int, default=128)
     t.add_argument("--steps", type=int, default=20)
     t.add_argument("--warmup", type=int, default=3)
+    t.add_argument("--graph", action="store_true", help="replay the whole training step as one CUDA graph")
     t.set_defaults(fn=train)
     i = sub.add_parser("infer")
     i.add_argument("--model", default="s", choices=["s", "lw"])
