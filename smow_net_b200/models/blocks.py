@@ -21,6 +21,49 @@ def _cyclic_frame_mix_composed(frames5d, shared, own):
     return torch.cat([kept[j] + lent[(j + 1) % 4] for j in range(4)], dim=2)
 
 
+_SIDE_STREAMS = {}
+
+
+class _Fork:
+    """Run independent pieces of one operator on side streams.  Only while a CUDA graph is being captured: the branches
+    become parallel nodes of the graph, so the small decoder levels (a 16-CTA GEMM each) overlap instead of queueing;
+    in eager mode the launch loop is the bottleneck and the context does nothing."""
+
+    def __init__(self, device, n):
+        self.active = torch.cuda.is_current_stream_capturing()
+        if not self.active:
+            return
+        key = device.index
+        pool = _SIDE_STREAMS.setdefault(key, [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device=device))
+        self.pool, self.main, self.done = pool, torch.cuda.current_stream(device), []
+        self.start = self.main.record_event()
+
+    def branch(self, i):
+        if not self.active:
+            import contextlib
+            return contextlib.nullcontext()
+        s = self.pool[i]
+        s.wait_event(self.start)
+        fork = self
+
+        class _Ctx:
+            def __enter__(self):
+                self.cm = torch.cuda.stream(s)
+                self.cm.__enter__()
+
+            def __exit__(self, *exc):
+                self.cm.__exit__(*exc)
+                fork.done.append(s.record_event())
+        return _Ctx()
+
+    def join(self):
+        if self.active:
+            for e in self.done:
+                self.main.wait_event(e)
+
+
 def _mix_matrix(conv):
     """(Cin, Cout) matrix of a 1x1x1 Conv3d (weight is Cout x Cin) or ConvTranspose3d (weight is Cin x Cout)."""
     w = conv.weight[:, :, 0, 0, 0]
@@ -46,9 +89,12 @@ class _CyclicMixGemm(torch.autograd.Function):
         torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
         try:
             Y = torch.mm(X.view(-1, Cin), w_shared).view(B, T, H * W, Cout)
+            fork = _Fork(x5.device, 4)                     # the four frames are independent
             for j in range(4):
                 k = (j + 1) % 4
-                Y[:, j].baddbmm_(X[:, k], ws[k].unsqueeze(0).expand(B, Cin, Cout))
+                with fork.branch(j):
+                    Y[:, j].baddbmm_(X[:, k], ws[k].unsqueeze(0).expand(B, Cin, Cout))
+            fork.join()
         finally:
             torch.backends.cuda.matmul.allow_tf32 = old
         if bias is not None:                                                 # (4, Cout): shared bias + own[j+1] bias
@@ -70,10 +116,13 @@ class _CyclicMixGemm(torch.autograd.Function):
             G2 = G.view(-1, Cout)
             gX = torch.mm(G2, w_shared.t()).view(B, T, H * W, Cin)
             gws = [None] * 4
+            fork = _Fork(gy5.device, 4)
             for j in range(4):
                 k = (j + 1) % 4
-                gX[:, k].baddbmm_(G[:, j], ws[k].t().unsqueeze(0).expand(B, Cout, Cin))
-                gws[k] = torch.bmm(X[:, k].transpose(1, 2), G[:, j]).sum(0)
+                with fork.branch(j):
+                    gX[:, k].baddbmm_(G[:, j], ws[k].t().unsqueeze(0).expand(B, Cout, Cin))
+                    gws[k] = torch.bmm(X[:, k].transpose(1, 2), G[:, j]).sum(0)
+            fork.join()
             # K = B*4*HW is huge and M = N = C tiny: one GEMM per (pair, frame) + a sum parallelises where cuBLAS's
             # single un-split GEMM does not (305 us -> ~40 us at the 128 x 128 level)
             g_shared = torch.bmm(X.view(B * T, H * W, Cin).transpose(1, 2), G.view(B * T, H * W, Cout)).sum(0)
