@@ -241,8 +241,8 @@ def main():
                                 else "hbm"} for k, v in summ.items()}
         # the dominant LAUNCH of the path BASELINE.json names (warp+stack and temporal
         # lerp+concat): launches of one operator differ by 300x in size across the decoder levels, so they are kept
-        # apart by shape; the tokenizer (row N2) is FP32-issue bound and is reported in all_kernels only
-        hot = {k: v for k, v in shapes.items() if not k.startswith("tokenizer")}
+        # apart by shape; the widened rows (N2 tokenizer: FP32-issue bound; N4 frame mix) are reported in all_kernels only
+        hot = {k: v for k, v in shapes.items() if k.startswith(("warp_", "tlerp_"))}      # rows N2 / N4: all_kernels only
         dom = max(hot, key=lambda k: hot[k]["ms"])
         roof = {"bound": "hbm", "kernel": dom.split("@")[0], "achieved": hot[dom]["gbps"], "peak": peak, "unit": "GB/s",
                 "frac": hot[dom]["gbps"] / peak, "traffic": ncu_traffic(dom.split("@")[0] + "@largest"), "peak_source": peak_src,

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SMOW_ABI_VERSION 3
+#define SMOW_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SMOW_API __attribute__((visibility("default")))
@@ -163,6 +163,23 @@ SMOW_API int smow_tokenizer_bwd(const float* gtokens, const void* x, const float
                        const float* tokens, const float* stats,
                        void* gx, float* gwa, float* gba, int B, int C, int64_t hw,
                        int dtype, int layout, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- N4: cyclic temporal frame mix of the decoder blocks -------------------------------------
+ * Replaces, for C_in = C_out = C in {16, 28, 32, 64} (the large decoder levels), the slice / ten 1x1x1
+ * convolutions / adds / concat of conv_trans_block_3d.forward and conv_block_2_3d.forward
+ * (models/SMOW_Net.py:121-139, models/SMOW_Net_LW.py:121-137,160-175):
+ *   out[b,f,p,:] = in[b,f,p,:] @ m0 + in[b,(f+shift)%4,p,:] @ m1[(f+own_off)%4]
+ * in / out: (B,C,4,H,W) fp32 NDHWC; m0 (C,C) and m1 (4,C,C): row = input channel, column = output channel.
+ *   forward  : m0 = W_shared, m1 = W_own,     shift = 1, own_off = 1
+ *   d(input) : m0 = W_shared^T, m1 = W_own^T, shift = 3, own_off = 0   (in = d out)
+ * smow_frame_mix_wgrad: gw (5,C,C) = dW_shared, dW_own[0..3] (overwritten); workspace of
+ * smow_frame_mix_wgrad_workspace_bytes(B,C,hw) bytes, uninitialised.  Fixed summation order.             */
+SMOW_API int     smow_frame_mix_supported(int C);
+SMOW_API int     smow_frame_mix_apply(const float* in, const float* m0, const float* m1, float* out,
+                         int B, int C, int64_t hw, int shift, int own_off, void* stream);
+SMOW_API int64_t smow_frame_mix_wgrad_workspace_bytes(int B, int C, int64_t hw);
+SMOW_API int     smow_frame_mix_wgrad(const float* x, const float* gy, float* gw, int B, int C, int64_t hw,
+                         void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -141,7 +141,13 @@ def cyclic_frame_mix(frames5d, shared, own):
     if shared.bias is not None:
         # out[j] = shared(f_j) + own[j+1](f_{j+1}): frame j carries the shared bias plus the bias of own[(j+1) % 4]
         bias = torch.stack([shared.bias + own[(j + 1) % 4].bias for j in range(4)])
-    return _CyclicMixGemm.apply(frames5d, _mix_matrix(shared), *[_mix_matrix(m) for m in own], bias)
+    w_shared = _mix_matrix(shared)
+    from .. import ops
+    if ops.frame_mix_supported(frames5d, w_shared.shape[1]):
+        # the large decoder levels (C = 16 / 28 / 32 / 64): one hand-written pass instead of five GEMM passes
+        y = ops.frame_mix(frames5d, w_shared, torch.stack([_mix_matrix(m) for m in own]))
+        return y if bias is None else y + bias.t().reshape(1, -1, 4, 1, 1)
+    return _CyclicMixGemm.apply(frames5d, w_shared, *[_mix_matrix(m) for m in own], bias)
 
 
 def _identity_1x1(conv):

@@ -443,3 +443,59 @@ def semantic_tokens(x, weight, bias):
     if x.shape[0] == 0:
         return x.new_zeros((0, 4, 8, x.shape[1])) + 0 * (x.sum() + weight.sum() + bias.sum())
     return _SemanticTokens.apply(x, weight, bias)
+
+
+# ----------------------------------------------------------------------------- N4: cyclic temporal frame mix
+def frame_mix_bytes(B, C, hw, s=4):
+    """Algorithmic bytes of one apply pass: the 4-frame tensor read once and written once."""
+    return 2 * B * 4 * C * hw * s
+
+
+class _FrameMix(torch.autograd.Function):
+    """y[:, :, j] = x[:, :, j] @ W_shared + x[:, :, (j+1) % 4] @ W_own[(j+1) % 4]  (matrices: rows = input channels)."""
+
+    @staticmethod
+    def forward(ctx, x, w_shared, w_own):
+        B, C, T, H, W = x.shape
+        x = x.contiguous(memory_format=torch.channels_last_3d)
+        m0, m1 = w_shared.contiguous().float(), w_own.contiguous().float()
+        y = torch.empty_like(x, memory_format=torch.channels_last_3d)
+        lib = _lib.load()
+        with torch.cuda.device_of(x):
+            _call("frame_mix_fwd", frame_mix_bytes(B, C, H * W), lib.smow_frame_mix_apply,
+                  x.data_ptr(), m0.data_ptr(), m1.data_ptr(), y.data_ptr(), B, C, H * W, 1, 1, _stream())
+        ctx.save_for_backward(x, m0, m1)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, m0, m1 = ctx.saved_tensors
+        B, C, T, H, W = x.shape
+        gy = gy.contiguous(memory_format=torch.channels_last_3d)
+        gx = torch.empty_like(x, memory_format=torch.channels_last_3d)
+        gw = torch.empty((5, C, C), dtype=torch.float32, device=x.device)
+        m0t, m1t = m0.t().contiguous(), m1.transpose(1, 2).contiguous()
+        lib = _lib.load()
+        n = int(lib.smow_frame_mix_wgrad_workspace_bytes(B, C, H * W))
+        ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device_of(x):
+            _call("frame_mix_bwd", frame_mix_bytes(B, C, H * W), lib.smow_frame_mix_apply,
+                  gy.data_ptr(), m0t.data_ptr(), m1t.data_ptr(), gx.data_ptr(), B, C, H * W, 3, 0, _stream())
+            _call("frame_mix_wgrad", frame_mix_bytes(B, C, H * W), lib.smow_frame_mix_wgrad,
+                  x.data_ptr(), gy.data_ptr(), gw.data_ptr(), B, C, H * W, ws.data_ptr(), n, _stream())
+        return gx, gw[0], gw[1:]
+
+
+def frame_mix_supported(x, c_out):
+    """True when the hand-written kernels take this tensor: CUDA fp32 (B,C,4,H,W) with C_in = C_out in {16,28,32,64}."""
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.shape[2] == 4 and x.shape[1] == c_out
+            and x.shape[0] > 0 and bool(_lib.load().smow_frame_mix_supported(int(c_out))))
+
+
+def frame_mix(x, w_shared, w_own):
+    """Cyclic temporal frame mix of the decoder blocks (reference models/SMOW_Net.py:121-139) in one pass:
+    x (B,C,4,H,W), w_shared (C,C), w_own (4,C,C) with rows = input channels -> (B,C,4,H,W), channels_last_3d."""
+    _require_cuda(x, w_shared, w_own)
+    if not frame_mix_supported(x, w_shared.shape[1]):
+        raise RuntimeError("frame_mix: built for fp32 (B,C,4,H,W) stacks with C_in = C_out in {16, 28, 32, 64}")
+    return _FrameMix.apply(x, w_shared, w_own)

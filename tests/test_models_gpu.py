@@ -132,27 +132,44 @@ def test_graphed_step_replays_the_eager_step(with_optimizer):
             assert float((ga[k] - gb[k]).abs().max()) <= 2e-4 * scale, k
 
 
-@pytest.mark.parametrize("kind", ["conv", "deconv_bias"])
-def test_cyclic_frame_mix_gemm_matches_the_composed_reference(kind):
-    """Row N4: the GEMM formulation of the frame mix (models/blocks.py) equals the reference's composition of slices,
-    1x1x1 convolutions, adds and a concat — outputs, input gradient and all ten parameter gradients."""
+@pytest.mark.parametrize("case", [("conv", 24, 24, 9, 7), ("deconv_bias", 20, 12, 9, 7),          # cuBLAS formulation
+                                  ("conv", 16, 16, 9, 7), ("conv", 16, 16, 128, 128), ("deconv_bias", 28, 28, 40, 37),
+                                  ("conv", 32, 32, 64, 64), ("deconv_bias", 64, 64, 32, 33), ("conv", 28, 28, 5, 3)])
+def test_cyclic_frame_mix_matches_the_composed_reference(case):
+    """Row N4: the hand-written frame-mix kernels (C = 16 / 28 / 32 / 64) and the GEMM formulation (other channel counts)
+    equal the reference's composition of slices, 1x1x1 convolutions, adds and a concat (models/SMOW_Net.py:121-139) —
+    outputs, input gradient and all parameter gradients."""
+    from smow_net_b200 import _lib
     from smow_net_b200.models import blocks
+    kind, cin, cout, H, W = case
     torch.manual_seed(3)
-    cin, cout = (24, 24) if kind == "conv" else (20, 12)
     mk = (lambda: torch.nn.Conv3d(cin, cout, 1, bias=False)) if kind == "conv" else \
          (lambda: torch.nn.ConvTranspose3d(cin, cout, 1, bias=True))
     mods = [mk().to(DEV) for _ in range(5)]
-    x = torch.randn(3, cin, 4, 9, 7, device=DEV).contiguous(memory_format=torch.channels_last_3d)
-    g = torch.randn(3, cout, 4, 9, 7, device=DEV)
-    res = []
+    B = 2 if H * W > 4096 else 3
+    x = torch.randn(B, cin, 4, H, W, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    g = torch.randn(B, cout, 4, H, W, device=DEV)
+    res, launches = [], []
     for fn in (blocks.cyclic_frame_mix, blocks._cyclic_frame_mix_composed):
         for m in mods:
             m.zero_grad(set_to_none=True)
         xi = x.clone(memory_format=torch.preserve_format).requires_grad_(True)
+        before = _lib.launch_count()
         y = fn(xi, mods[4], mods[:4])
         y.backward(g)
+        launches.append(_lib.launch_count() - before)
         res.append([y.detach(), xi.grad] + [p.grad.clone() for m in mods for p in m.parameters()])
+    fused = cin == cout and cin in (16, 28, 32, 64)
+    assert launches == [4 if fused else 0, 0]          # apply fwd + apply bwd + wgrad (2 kernels)
     assert res[0][0].is_contiguous(memory_format=torch.channels_last_3d)
     for a, b in zip(*res):
         assert a.shape == b.shape
         assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(b.abs().max()))
+    if fused:       # fixed summation order: bit-reproducible
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        xi = x.clone(memory_format=torch.preserve_format).requires_grad_(True)
+        y = blocks.cyclic_frame_mix(xi, mods[4], mods[:4])
+        y.backward(g)
+        again = [y.detach(), xi.grad] + [p.grad.clone() for m in mods for p in m.parameters()]
+        assert all(torch.equal(a, b) for a, b in zip(res[0], again))
