@@ -238,7 +238,8 @@ def main():
                        "algorithmic_GB_per_s": v["gbps"], "frac_of_peak": v["gbps"] / peak,
                        "ms_per_step": v["ms"] / n_kt,
                        "bound": "fp32 issue (~300 FP32 instructions per 64-byte pixel), not HBM" if k.startswith("tokenizer")
-                                else "hbm"} for k, v in summ.items()}
+                                else "hbm", "row": "N2" if k.startswith("tokenizer") else "N4" if k.startswith("frame_mix")
+                                else "A1-A5"} for k, v in summ.items()}
         # the dominant LAUNCH of the path BASELINE.json names (warp+stack and temporal
         # lerp+concat): launches of one operator differ by 300x in size across the decoder levels, so they are kept
         # apart by shape; the widened rows (N2 tokenizer: FP32-issue bound; N4 frame mix) are reported in all_kernels only

@@ -48,6 +48,10 @@ def main():
                 bias = torch.zeros(8, device=dev, requires_grad=True)
                 stack = dec.detach().requires_grad_(True)
                 ops.semantic_tokens(stack, w, bias).backward(torch.randn(a.B, 4, 8, a.C, device=dev, generator=g))
+                if ops.frame_mix_supported(dec, a.C):      # row N4: cyclic frame mix (apply fwd, apply d-input, weight grads)
+                    ws_ = (torch.randn(a.C, a.C, device=dev, generator=g) / a.C ** 0.5).requires_grad_(True)
+                    wo_ = (torch.randn(4, a.C, a.C, device=dev, generator=g) / a.C ** 0.5).requires_grad_(True)
+                    ops.frame_mix(dec.detach().requires_grad_(True), ws_, wo_).backward(gout)
             torch.cuda.synchronize()
         print(i, {k: "%.3f ms %.0f GB/s" % (v["ms"], v["gbps"]) for k, v in kt.summary().items()})
 

@@ -116,7 +116,7 @@ def kernels(tag):
                 continue
             rows = ncu_raw(rep)
             f.write("\n## %s\n\n| # | kernel | %s |\n|---|---|%s\n" % (title, " | ".join(t for _, t in METRICS), "---:|" * len(METRICS)))
-            rows = [d for d in rows if d["name"].startswith(("warp_", "tlerp_", "tok_"))]
+            rows = [d for d in rows if d["name"].startswith(("warp_", "tlerp_", "tok_", "mix_"))]
             for i, d in enumerate(rows):
                 cells = []
                 for m, _ in METRICS:
@@ -142,7 +142,8 @@ def kernels(tag):
     if traffic:
         op_of = {"warp_fwd": "warp_stack_fwd", "warp_stack_fwd": "warp_stack_fwd", "warp_bwd": "warp_stack_bwd",
                  "warp_stack_bwd": "warp_stack_bwd", "tlerp_cat_fwd": "tlerp_cat_fwd", "tlerp_cat_bwd": "tlerp_cat_bwd",
-                 "tok_fwd": "tokenizer_fwd", "tok_bwd": "tokenizer_bwd"}
+                 "tok_fwd": "tokenizer_fwd", "tok_bwd": "tokenizer_bwd", "mix_apply": "frame_mix_apply",
+                 "mix_wgrad": "frame_mix_wgrad"}
         per_op = {}
         for k, (n, b, bmax) in traffic.items():
             for pre, op in op_of.items():
