@@ -72,11 +72,12 @@ def launches(tag):
         f.write("%d launches, %.1f ms of kernel time in total.\n\n| kernel | launches | us | share |\n|---|---:|---:|---:|\n" % (n, total / 1e3))
         ours = 0.0
         for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            mine = k.startswith(("warp_", "tlerp_"))
+            mine = k.startswith(("warp_", "tlerp_", "tok_", "mix_"))
             ours += us if mine else 0
             if us / total >= 0.003 or mine:
                 f.write("| %s%s | %d | %.1f | %.2f %% |\n" % ("**" if mine else "", k + ("**" if mine else ""), c, us, 100 * us / total))
-        f.write("\nHand-written hot-path kernels: %.1f us = %.2f %% of the step's kernel time.\n" % (ours, 100 * ours / total))
+        f.write("\nHand-written kernels (rows A1-A5: warp_*, tlerp_*; N2: tok_*; N4: mix_*): %.1f us = %.2f %% of the step's "
+                "kernel time.\n" % (ours, 100 * ours / total))
 
 
 def ncu_raw(rep):
