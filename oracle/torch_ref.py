@@ -73,3 +73,19 @@ def ref_semantic_tokens(x, weight, bias):
         attn = torch.softmax(F.conv2d(frame, weight, bias).reshape(b, weight.shape[0], -1), dim=-1)
         out.append(torch.einsum("bln,bcn->blc", attn, frame.reshape(b, c, -1)))
     return torch.stack(out, 1)
+
+
+def ref_cyclic_frame_mix(frames, w_shared, w_own, bias=None):
+    """Matrix restatement of the decoder's temporal frame mix (reference models/SMOW_Net.py:121-139,
+    models/SMOW_Net_LW.py:119-137,160-175):  out[:, :, j] = W5 . T_j + W_{j+1} . T_{j+1}  (indices mod 4), i.e.
+    `T1_F1 + T2_F2, T2_F1 + T3_F2, T3_F1 + T4_F2, T4_F1 + T1_F2` with *_F1 = conv3d_time_5 and Tk_F2 = conv3d_time_k.
+    frames (B,Cin,4,H,W); w_shared (Cin,Cout) and w_own (4,Cin,Cout) with rows = input channels (a Conv3d weight
+    transposed, a ConvTranspose3d weight as stored); bias (4,Cout) = shared bias + bias of own[(j+1) % 4], or None."""
+    out = []
+    for j in range(4):
+        k = (j + 1) % 4
+        y = torch.einsum("bchw,cd->bdhw", frames[:, :, j], w_shared) + torch.einsum("bchw,cd->bdhw", frames[:, :, k], w_own[k])
+        if bias is not None:
+            y = y + bias[j].view(1, -1, 1, 1)
+        out.append(y)
+    return torch.stack(out, 2)
