@@ -83,3 +83,27 @@ def tlerp_cat_bwd(gcat, Cd):
     gskip = np.empty((B, Cs, 2, h, w), np.float32)
     _load().smow_oracle_tlerp_cat_bwd(_p(gcat), _p(gskip), B, Cd, Cs, ctypes.c_int64(h * w))
     return gskip
+
+
+def tokenizer_fwd(x, wa, ba):
+    """Row N2 (reference models/SMOW_Net.py:176-187): x (B,C,4,H,W), wa (L,C[,1,1]), ba (L,) -> tokens (B,4,L,C)."""
+    x, wa, ba = _f32(x), _f32(np.asarray(wa).reshape(np.asarray(wa).shape[0], -1)), _f32(ba)
+    B, C, T, H, W = x.shape
+    assert T == 4 and wa.shape[1] == C and C <= 512
+    L = wa.shape[0]
+    tokens = np.empty((B, 4, L, C), np.float32)
+    _load().smow_oracle_tokenizer_fwd(_p(x), _p(wa), _p(ba), _p(tokens), B, C, L, ctypes.c_int64(H * W))
+    return tokens
+
+
+def frame_mix_fwd(x, w_shared, w_own, bias=None):
+    """Row N4 (reference models/SMOW_Net.py:121-139): x (B,Cin,4,H,W), w_shared (Cin,Cout), w_own (4,Cin,Cout) with
+    rows = input channels, bias (4,Cout) or None -> (B,Cout,4,H,W)."""
+    x, ws, wo = _f32(x), _f32(w_shared), _f32(w_own)
+    B, Cin, T, H, W = x.shape
+    Cout = ws.shape[1]
+    assert T == 4 and ws.shape == (Cin, Cout) and wo.shape == (4, Cin, Cout)
+    bias = None if bias is None else _f32(bias)
+    out = np.empty((B, Cout, 4, H, W), np.float32)
+    _load().smow_oracle_frame_mix_fwd(_p(x), _p(ws), _p(wo), _p(bias), _p(out), B, Cin, Cout, ctypes.c_int64(H * W))
+    return out

@@ -186,3 +186,61 @@ API void smow_oracle_tlerp_cat_bwd(const float* gcat, float* gskip, int B, int C
       }
     }
 }
+
+/* ---- row N2: semantic tokenizer --------------------------------------------------------------
+ * models/SMOW_Net.py:176-187 (= models/SMOW_Net_LW.py:195-206), per pair b and frame k:
+ *   spatial_attention = conv_a(x_t)            1x1 conv C -> L:  logit[l][p] = sum_c wa[l][c] x[c][p] + ba[l]
+ *   softmax over the H*W pixels (dim = -1)      ATen: max, exp(x - max), sum, divide
+ *   tokens = einsum('bln,bcn->blc')            tokens[l][c] = sum_p attn[l][p] x[c][p]
+ * x (B,C,4,hw) NCDHW contiguous; tokens (B,4,L,C).  Double accumulation: this is the checker. */
+API void smow_oracle_tokenizer_fwd(const float* x, const float* wa, const float* ba, float* tokens, int B, int C,
+                                   int L, int64_t hw) {
+#pragma omp parallel for collapse(2)
+  for (int b = 0; b < B; ++b)
+    for (int k = 0; k < 4; ++k)
+      for (int l = 0; l < L; ++l) {
+        const float* xb = x + (((int64_t)b * C) * 4 + k) * hw;      /* channel c at + c*4*hw */
+        double mx = -INFINITY;
+        for (int64_t p = 0; p < hw; ++p) {
+          double lg = ba[l];
+          for (int c = 0; c < C; ++c) lg += (double)wa[l * C + c] * xb[(int64_t)c * 4 * hw + p];
+          if (lg > mx) mx = lg;
+        }
+        double s = 0.0;
+        double acc[512];                                            /* C <= 512, checked by the Python front-end */
+        for (int c = 0; c < C; ++c) acc[c] = 0.0;
+        for (int64_t p = 0; p < hw; ++p) {
+          double lg = ba[l];
+          for (int c = 0; c < C; ++c) lg += (double)wa[l * C + c] * xb[(int64_t)c * 4 * hw + p];
+          const double e = exp(lg - mx);
+          s += e;
+          for (int c = 0; c < C; ++c) acc[c] += e * xb[(int64_t)c * 4 * hw + p];
+        }
+        for (int c = 0; c < C; ++c) tokens[(((int64_t)b * 4 + k) * L + l) * C + c] = (float)(acc[c] / s);
+      }
+}
+
+/* ---- row N4: cyclic temporal frame mix -------------------------------------------------------
+ * models/SMOW_Net.py:121-139 (= models/SMOW_Net_LW.py:119-137, 160-175):
+ *   x = cat([T1_F1 + T2_F2, T2_F1 + T3_F2, T3_F1 + T4_F2, T4_F1 + T1_F2], dim=2)
+ * with Tk_F1 = conv3d_time_5(Tk) (shared) and Tk_F2 = conv3d_time_k(Tk) (own), all 1x1x1:
+ *   out[b][d][j][p] = sum_c x[b][c][j][p] ws[c][d] + sum_c x[b][c][(j+1)%4][p] wo[(j+1)%4][c][d] (+ bias[j][d])
+ * x (B,Cin,4,hw), out (B,Cout,4,hw) NCDHW contiguous; ws (Cin,Cout), wo (4,Cin,Cout): rows = input channels;
+ * bias (4,Cout) or NULL. */
+API void smow_oracle_frame_mix_fwd(const float* x, const float* ws, const float* wo, const float* bias, float* out,
+                                   int B, int Cin, int Cout, int64_t hw) {
+#pragma omp parallel for collapse(2)
+  for (int b = 0; b < B; ++b)
+    for (int d = 0; d < Cout; ++d)
+      for (int j = 0; j < 4; ++j) {
+        const int k = (j + 1) % 4;
+        for (int64_t p = 0; p < hw; ++p) {
+          double a = bias ? (double)bias[j * Cout + d] : 0.0;
+          for (int c = 0; c < Cin; ++c) {
+            a += (double)x[(((int64_t)b * Cin + c) * 4 + j) * hw + p] * ws[c * Cout + d];
+            a += (double)x[(((int64_t)b * Cin + c) * 4 + k) * hw + p] * wo[((int64_t)k * Cin + c) * Cout + d];
+          }
+          out[(((int64_t)b * Cout + d) * 4 + j) * hw + p] = (float)a;
+        }
+      }
+}

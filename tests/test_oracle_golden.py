@@ -75,3 +75,21 @@ def test_border_gradient_gates():
     assert np.all(gflow == 0)
     mine = c_oracle.warp_stack_bwd(z["warp/all_clamped/gout"], z["warp/all_clamped/x"], z["warp/all_clamped/flow"])[1]
     assert np.all(mine == 0)
+
+
+def test_c_oracle_tokenizer_and_frame_mix_match_the_torch_restatements():
+    """Rows N2 / N4: the plain-C restatements (oracle/smow_oracle.c) agree with the ATen-call restatements
+    (oracle/torch_ref.py) that tests/test_models_cpu.py pins against the real reference's modules."""
+    import torch
+    from oracle import c_oracle, torch_ref
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 8, 4, 7, 9, generator=g)
+    wa, ba = torch.randn(8, 8, 1, 1, generator=g) * 0.5, torch.randn(8, generator=g)
+    tok = c_oracle.tokenizer_fwd(x.numpy(), wa.numpy(), ba.numpy())
+    ref = torch_ref.ref_semantic_tokens(x.double(), wa.double(), ba.double()).numpy()
+    assert np.abs(tok - ref).max() <= 1e-6
+    ws, wo, bias = torch.randn(8, 6, generator=g), torch.randn(4, 8, 6, generator=g), torch.randn(4, 6, generator=g)
+    for bb in (None, bias):
+        got = c_oracle.frame_mix_fwd(x.numpy(), ws.numpy(), wo.numpy(), None if bb is None else bb.numpy())
+        want = torch_ref.ref_cyclic_frame_mix(x.double(), ws.double(), wo.double(), None if bb is None else bb.double()).numpy()
+        assert np.abs(got - want).max() <= 1e-5
