@@ -93,3 +93,15 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_widened_operators_have_no_cpu_path_either():
+    """Rows N2 / N4: like the warp and lerp operators, ops.semantic_tokens and ops.frame_mix refuse CPU tensors instead
+    of falling back (the modules keep the reference's own PyTorch composition for CPU tensors; the operators do not)."""
+    x = torch.zeros(1, 16, 4, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.semantic_tokens(x, torch.zeros(8, 16, 1, 1), torch.zeros(8))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.frame_mix(x, torch.zeros(16, 16), torch.zeros(4, 16, 16))
+    assert _lib.load().smow_frame_mix_supported(28) == 1 and _lib.load().smow_frame_mix_supported(24) == 0
+    assert _lib.load().smow_tokenizer_workspace_bytes(2, 16, 16384) == 4 * 2 * 32 * (16 + 8 * 16) * 4
