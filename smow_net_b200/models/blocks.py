@@ -76,8 +76,8 @@ class _CyclicMixGemm(torch.autograd.Function):
     In NDHWC memory a frame of one pair is a dense (HW, C) matrix, so with X = (B, 4, HW, Cin):
         Y           = X @ W_shared                      one GEMM over all four frames
         Y[:, j]    += X[:, (j+1) % 4] @ W_own[j+1]      four strided-batched GEMMs accumulating in place
-    and the backward is the transposed set.  The 1x1x1 convolutions this replaces ran on cuDNN under
-    torch.backends.cudnn.allow_tf32, so that flag also decides whether these GEMMs may use TF32."""
+    and the backward is the transposed set.  The GEMMs follow torch.backends.cuda.matmul.allow_tf32 as the process set it
+    (fp32 by default); the global flag is never toggled per call — autograd worker threads share it."""
 
     @staticmethod
     def forward(ctx, x5, w_shared, w0, w1, w2, w3, bias):
@@ -85,18 +85,13 @@ class _CyclicMixGemm(torch.autograd.Function):
         X = x5.permute(0, 2, 3, 4, 1).reshape(B, T, H * W, Cin)          # a view: x5 is channels_last_3d
         ws = (w0, w1, w2, w3)
         Cout = w_shared.shape[1]
-        old = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
-        try:
-            Y = torch.mm(X.view(-1, Cin), w_shared).view(B, T, H * W, Cout)
-            fork = _Fork(x5.device, 4)                     # the four frames are independent
-            for j in range(4):
-                k = (j + 1) % 4
-                with fork.branch(j):
-                    Y[:, j].baddbmm_(X[:, k], ws[k].unsqueeze(0).expand(B, Cin, Cout))
-            fork.join()
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = old
+        Y = torch.mm(X.view(-1, Cin), w_shared).view(B, T, H * W, Cout)
+        fork = _Fork(x5.device, 4)                     # the four frames are independent
+        for j in range(4):
+            k = (j + 1) % 4
+            with fork.branch(j):
+                Y[:, j].baddbmm_(X[:, k], ws[k].unsqueeze(0).expand(B, Cin, Cout))
+        fork.join()
         if bias is not None:                                                 # (4, Cout): shared bias + own[j+1] bias
             Y.add_(bias.view(1, T, 1, Cout))
         ctx.save_for_backward(X, w_shared, w0, w1, w2, w3)
@@ -110,24 +105,19 @@ class _CyclicMixGemm(torch.autograd.Function):
         B, Cin, Cout, T, H, W = ctx.dims
         ws = (w0, w1, w2, w3)
         G = gy5.contiguous(memory_format=torch.channels_last_3d).permute(0, 2, 3, 4, 1).reshape(B, T, H * W, Cout)
-        old = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
-        try:
-            G2 = G.view(-1, Cout)
-            gX = torch.mm(G2, w_shared.t()).view(B, T, H * W, Cin)
-            gws = [None] * 4
-            fork = _Fork(gy5.device, 4)
-            for j in range(4):
-                k = (j + 1) % 4
-                with fork.branch(j):
-                    gX[:, k].baddbmm_(G[:, j], ws[k].t().unsqueeze(0).expand(B, Cout, Cin))
-                    gws[k] = torch.bmm(X[:, k].transpose(1, 2), G[:, j]).sum(0)
-            fork.join()
-            # K = B*4*HW is huge and M = N = C tiny: one GEMM per (pair, frame) + a sum parallelises where cuBLAS's
-            # single un-split GEMM does not (305 us -> ~40 us at the 128 x 128 level)
-            g_shared = torch.bmm(X.view(B * T, H * W, Cin).transpose(1, 2), G.view(B * T, H * W, Cout)).sum(0)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = old
+        G2 = G.view(-1, Cout)
+        gX = torch.mm(G2, w_shared.t()).view(B, T, H * W, Cin)
+        gws = [None] * 4
+        fork = _Fork(gy5.device, 4)
+        for j in range(4):
+            k = (j + 1) % 4
+            with fork.branch(j):
+                gX[:, k].baddbmm_(G[:, j], ws[k].t().unsqueeze(0).expand(B, Cout, Cin))
+                gws[k] = torch.bmm(X[:, k].transpose(1, 2), G[:, j]).sum(0)
+        fork.join()
+        # K = B*4*HW is huge and M = N = C tiny: one GEMM per (pair, frame) + a sum parallelises where cuBLAS's
+        # single un-split GEMM does not (305 us -> ~40 us at the 128 x 128 level)
+        g_shared = torch.bmm(X.view(B * T, H * W, Cin).transpose(1, 2), G.view(B * T, H * W, Cout)).sum(0)
         gbias = G.sum(dim=(0, 2)) if ctx.has_bias else None               # (4, Cout)
         return gX.view(B, T, H, W, Cin).permute(0, 4, 1, 2, 3), g_shared, gws[0], gws[1], gws[2], gws[3], gbias
 
@@ -238,7 +228,10 @@ def convs_channels_last_3d(module):
     38.1 -> 33.6 ms (SMOW_Net_LW) per batch-16 step on B200 (benchmarks/e2e_probe.py).  Shapes, names and values
     of the parameters are untouched, so state_dicts stay interchangeable with the reference."""
     for p in module.parameters():
-        if p.dim() == 5:
+        # 1x1x1 kernels are left alone: for them both memory formats describe the same bytes, and re-striding the
+        # parameter only makes autograd's (contiguous-strided) gradient disagree with DDP's bucket view ("Grad strides
+        # do not match bucket view strides": one extra copy per such gradient inside the reducer)
+        if p.dim() == 5 and tuple(p.shape[2:]) != (1, 1, 1):
             p.data = p.data.contiguous(memory_format=torch.channels_last_3d)
     return module
 

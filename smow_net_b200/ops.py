@@ -22,11 +22,20 @@ _DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
 
 # ----------------------------------------------------------------------------- helpers
 def _require_cuda(*tensors):
+    """Every operand is a CUDA tensor and all of them live on ONE device (the C ABI takes raw pointers and launches on
+    the current device: it cannot catch either mistake)."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError(
                 "smow_net_b200 operators run on CUDA tensors only (hand-written sm_100a kernels, "
                 "no CPU fallback); got a %s tensor" % t.device)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("smow_net_b200: operands on different devices (%s and %s)" % (dev, t.device))
 
 
 def _dtype_code(t):
@@ -330,6 +339,8 @@ class _TLerpPairCat(torch.autograd.Function):
         if dec is not None:
             if dec.dim() != 5 or dec.shape[0] != B or dec.shape[2] != 4 or tuple(dec.shape[3:]) != (h, w):
                 raise RuntimeError("tlerp_pair_cat: dec must be (B,Cd,4,h,w) matching the frames")
+            if dec.dtype != a.dtype:
+                raise RuntimeError("tlerp_pair_cat: dec and frame dtypes differ (%s vs %s)" % (dec.dtype, a.dtype))
             Cd = dec.shape[1]
         a, layout = _layout5(a if dec is None or not _is_channels_last(dec) else
                              a.contiguous(memory_format=torch.channels_last), Cd, Cs)
@@ -496,6 +507,12 @@ def frame_mix(x, w_shared, w_own):
     """Cyclic temporal frame mix of the decoder blocks (reference models/SMOW_Net.py:121-139) in one pass:
     x (B,C,4,H,W), w_shared (C,C), w_own (4,C,C) with rows = input channels -> (B,C,4,H,W), channels_last_3d."""
     _require_cuda(x, w_shared, w_own)
-    if not frame_mix_supported(x, w_shared.shape[1]):
+    if w_shared.dim() != 2 or not frame_mix_supported(x, w_shared.shape[1]):
         raise RuntimeError("frame_mix: built for fp32 (B,C,4,H,W) stacks with C_in = C_out in {16, 28, 32, 64}")
+    C = x.shape[1]
+    if tuple(w_shared.shape) != (C, C) or tuple(w_own.shape) != (4, C, C):
+        raise RuntimeError("frame_mix: w_shared must be (C,C)=%s and w_own (4,C,C), got %s and %s"
+                           % ((C, C), tuple(w_shared.shape), tuple(w_own.shape)))
+    if w_shared.dtype != torch.float32 or w_own.dtype != torch.float32:
+        raise RuntimeError("frame_mix: fp32 matrices only")
     return _FrameMix.apply(x, w_shared, w_own)

@@ -55,9 +55,26 @@ def build_model(kind, device, pretrained=False):
     return model.to(device)
 
 
+def align_pointwise_grad_strides(model):
+    """1x1 (/1x1x1) convolution weights: both memory formats describe the same bytes, and cuDNN's NHWC weight-gradient
+    kernels hand back the channels-last spelling (strides (Cin,1,Cin,Cin)) while the parameter carries the contiguous
+    one (Cin,1,1,1).  DDP's reducer then warns "Grad strides do not match bucket view strides" and COPIES every such
+    gradient into its bucket view.  A tensor hook re-spells the gradient's strides as the parameter's (a view of the same
+    memory, no kernel), so gradient_as_bucket_view stays zero-copy."""
+    for p in model.parameters():
+        if p.requires_grad and p.dim() >= 4 and all(int(k) == 1 for k in p.shape[2:]):
+            def fix(g, p=p):
+                if g.stride() != p.stride() and g.is_contiguous():
+                    return g.as_strided(g.shape, p.stride(), g.storage_offset())
+                return g
+            p.register_hook(fix)
+    return model
+
+
 def wrap_ddp(model, device, world):
     if world == 1:
         return model
+    align_pointwise_grad_strides(model)
     from torch.nn.parallel import DistributedDataParallel as DDP
     ids = [device.index] if device.type == "cuda" else None
     # per-replica BatchNorm statistics (no SyncBN, no buffer broadcast) — the reference's regime
@@ -65,7 +82,7 @@ def wrap_ddp(model, device, world):
     # (the default 25 MB would leave SMOW_Net_LW with a single, un-overlapped all-reduce at the very end)
     cap = float(os.environ.get("SMOW_DDP_BUCKET_MB", "8"))
     return DDP(model, device_ids=ids, broadcast_buffers=False, gradient_as_bucket_view=True, bucket_cap_mb=cap,
-               static_graph=os.environ.get("SMOW_DDP_STATIC", "0") == "1")
+               static_graph=os.environ.get("SMOW_DDP_STATIC", "1") == "1")
 
 
 def max_over_ranks(value, device, world):

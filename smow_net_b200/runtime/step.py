@@ -8,8 +8,9 @@ import torch.nn.functional as F
 
 def bce_dice_loss(pred, true, eps=1e-7):
     """utils/loss_f.py:8-18: BCELoss(pred, true) + 1 - global dice."""
-    inter = (true * pred).sum()
-    return F.binary_cross_entropy(pred, true) + 1 - (2 * inter + eps) / (true.sum() + pred.sum() + eps)
+    bce = F.binary_cross_entropy(pred, true)          # first, like the reference: autograd then sums the three gradient
+    inter = (true * pred).sum()                       # contributions to `pred` in the same order (bit-identical grads)
+    return bce + 1 - (2 * inter + eps) / (true.sum() + pred.sum() + eps)
 
 
 def clip_gradient_(params, clip):
