@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SMOW_ABI_VERSION 4
+#define SMOW_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define SMOW_API __attribute__((visibility("default")))
@@ -180,6 +180,33 @@ SMOW_API int     smow_frame_mix_apply(const float* in, const float* m0, const fl
 SMOW_API int64_t smow_frame_mix_wgrad_workspace_bytes(int B, int C, int64_t hw);
 SMOW_API int     smow_frame_mix_wgrad(const float* x, const float* gy, float* gw, int B, int C, int64_t hw,
                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- N4 on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulator in tensor memory, TMA tile loads
+ * and stores).  Same operation as smow_frame_mix_apply, generalised:
+ *   out[b,f,p,0:C] = in[b,f,p,:] @ W_0 + in[b,(f+shift)%T,p,:] @ W_{1+(f+own_off)%T}  (+ bias[f,:])
+ *   T = 4: decoder blocks (models/SMOW_Net.py:121-139, models/SMOW_Net_LW.py:119-137,160-175);
+ *   T = 2: the encoder's Decompose_conv temporal exchange (models/SMOW_Net.py:460-473).
+ *   in     (B,C,T,H,W) fp32 NDHWC, dense
+ *   wpack  (1+T, C_out, C_in) fp32: matrix m as [output channel][input channel] (a Conv3d 1x1x1 weight as stored;
+ *          a ConvTranspose3d weight transposed); for d(input) pass the transposed matrices, shift = T-1, own_off = 0
+ *   bias   (T, C) or NULL
+ *   out    rows of `out_pitch` floats per pixel (out_pitch >= C, multiple of 4): out_pitch > C writes the result
+ *          straight into channels [0,C) of the decoder's concat buffer (rows A3+A4: models/SMOW_Net.py:78-94), the
+ *          buffer smow_tlerp_cat_fwd then completes with dec == NULL.
+ *   C in {16, 28, 32k (k <= 8), 320, 384, 448, 512}.  Arithmetic: TF32 products (10-bit mantissa), fp32 accumulation —
+ *   what cuDNN runs the reference's 1x1x1 convolutions in under torch.backends.cudnn.allow_tf32 = True.        */
+SMOW_API int smow_frame_mix_tc_supported(int C, int T);
+SMOW_API int smow_frame_mix_apply_tc(const float* in, const float* wpack, const float* bias, float* out,
+                         int B, int C, int T, int64_t hw, int64_t out_pitch, int shift, int own_off, void* stream);
+/* Weight gradients of the same operation on the tensor cores (M = input channels, N = output channels, K = pixels;
+ * the NDHWC tiles are MN-major operands as TMA delivers them, nothing is transposed):
+ *   gw[0]     = sum_{b,f} x[b,f]^T gy[b,f]                      (dW_0, row = input channel, column = output channel)
+ *   gw[1+g]   = sum_b x[b,(f+shift)%T]^T gy[b,f],  g = (f+own_off)%T
+ * x, gy (B,C,T,H,W) fp32 NDHWC dense; gw (1+T, C, C) overwritten; workspace of
+ * smow_frame_mix_wgrad_tc_workspace_bytes(B,C,T,hw) bytes (per-CTA partials, added in index order: deterministic). */
+SMOW_API int64_t smow_frame_mix_wgrad_tc_workspace_bytes(int B, int C, int T, int64_t hw);
+SMOW_API int smow_frame_mix_wgrad_tc(const float* x, const float* gy, float* gw, int B, int C, int T, int64_t hw,
+                         int shift, int own_off, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

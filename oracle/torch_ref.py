@@ -75,17 +75,20 @@ def ref_semantic_tokens(x, weight, bias):
     return torch.stack(out, 1)
 
 
-def ref_cyclic_frame_mix(frames, w_shared, w_own, bias=None):
-    """Matrix restatement of the decoder's temporal frame mix (reference models/SMOW_Net.py:121-139,
-    models/SMOW_Net_LW.py:119-137,160-175):  out[:, :, j] = W5 . T_j + W_{j+1} . T_{j+1}  (indices mod 4), i.e.
-    `T1_F1 + T2_F2, T2_F1 + T3_F2, T3_F1 + T4_F2, T4_F1 + T1_F2` with *_F1 = conv3d_time_5 and Tk_F2 = conv3d_time_k.
-    frames (B,Cin,4,H,W); w_shared (Cin,Cout) and w_own (4,Cin,Cout) with rows = input channels (a Conv3d weight
-    transposed, a ConvTranspose3d weight as stored); bias (4,Cout) = shared bias + bias of own[(j+1) % 4], or None."""
+def ref_cyclic_frame_mix(frames, w_shared, w_own, bias=None, shift=1, own_off=1):
+    """Matrix restatement of the temporal frame mix.  Decoder blocks (reference models/SMOW_Net.py:121-139,
+    models/SMOW_Net_LW.py:119-137,160-175), T = 4, shift = own_off = 1:  out[:, :, j] = W5 . T_j + W_{j+1} . T_{j+1}
+    (indices mod 4), i.e. `T1_F1 + T2_F2, T2_F1 + T3_F2, T3_F1 + T4_F2, T4_F1 + T1_F2` with *_F1 = conv3d_time_5 and
+    Tk_F2 = conv3d_time_k.  Encoder Decompose_conv (reference models/SMOW_Net.py:460-473), T = 2, shift = 1, own_off = 0,
+    w_own = [time_3, time_1]:  out[T1] = time_2(T1) + time_3(T2),  out[T2] = time_2(T2) + time_1(T1).
+    frames (B,Cin,T,H,W); w_shared (Cin,Cout) and w_own (T,Cin,Cout) with rows = input channels (a Conv3d weight
+    transposed, a ConvTranspose3d weight as stored); bias (T,Cout) = shared bias + bias of the own conv feeding frame f."""
+    T = w_own.shape[0]
     out = []
-    for j in range(4):
-        k = (j + 1) % 4
-        y = torch.einsum("bchw,cd->bdhw", frames[:, :, j], w_shared) + torch.einsum("bchw,cd->bdhw", frames[:, :, k], w_own[k])
+    for f in range(T):
+        g, k = (f + own_off) % T, (f + shift) % T
+        y = torch.einsum("bchw,cd->bdhw", frames[:, :, f], w_shared) + torch.einsum("bchw,cd->bdhw", frames[:, :, k], w_own[g])
         if bias is not None:
-            y = y + bias[j].view(1, -1, 1, 1)
+            y = y + bias[f].view(1, -1, 1, 1)
         out.append(y)
     return torch.stack(out, 2)

@@ -22,6 +22,7 @@ static Knob g_knobs[OPT_COUNT] = {
     {"bwd_chunk_mb", {0}},       // NDHWC scatter: process the batch in chunks of about this many MB (0 = whole batch)
     {"ndhwc_bwd_rows", {0}},     // NDHWC tile gather: rows per tile (0 = auto, about 512 pixels per tile)
     {"ndhwc_bwd_pf", {-1}},      // NDHWC tile gather: L2 prefetch distance in tiles (-1 = auto: 4 per SM, 0 = off)
+    {"tc_debug", {0}},           // bring-up switches of the tcgen05 kernels (0 in production)
 };
 
 int fail(int code, const char* fmt, ...) {

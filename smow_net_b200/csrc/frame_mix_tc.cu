@@ -1,0 +1,495 @@
+// Row N4 on Blackwell tensor cores: the temporal frame mix of the decoder blocks
+// (reference models/SMOW_Net.py:121-139, models/SMOW_Net_LW.py:119-137,160-175) and of the encoder's Decompose_conv
+// (models/SMOW_Net.py:460-473) as a TMA-fed tcgen05 GEMM with the accumulator in tensor memory:
+//
+//     out[b, f, p, :] = in[b, f, p, :] @ W_0  +  in[b, (f + shift) % T, p, :] @ W_{1 + (f + own_off) % T}   (+ bias[f, :])
+//
+// T = 4 (decoder: cyclic exchange between the four frames) or T = 2 (encoder: T1 <-> T2 exchange).  In NDHWC memory a
+// frame of one pair is a dense (pixels, C) matrix, so one CTA computes D[128 pixels, Nc] = A[128, 2C] * B[2C, Nc]:
+//   * A tiles (128 pixels x 32 channels fp32 = 16 KB) arrive by TMA (cp.async.bulk.tensor, 128-byte swizzle) from the two
+//     source frames; B tiles (Nc output channels x 32 input channels, K-major) from the packed weights wpack
+//     [(1 + T), C_out, C_in]; a ring of up to 4 stages guarded by mbarriers;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = Nc, K = 8) per 8 channels,
+//     accumulating in TMEM; tcgen05.commit frees the stage / publishes the accumulator;
+//   * epilogue: 4 warps read their 32 TMEM lanes with tcgen05.ld, add the bias, stage the tile in shared memory in the
+//     TMA swizzle pattern (conflict-free 16-byte stores) and one thread issues the TMA store.  The store's tensor map
+//     describes a channel slice [0, C) of rows `out_pitch` floats apart, so the result can be written STRAIGHT INTO the
+//     decoder's concat buffer (rows A3 + A4): the `dec` half is never copied.
+// Channel counts that are not a multiple of 32 (16, 28) use the same 32-wide tiles: TMA zero-fills what lies outside
+// the tensor and clips the store.  TF32 (10-bit mantissa) is the precision class the reference's own 1x1x1
+// convolutions run in under torch.backends.cudnn.allow_tf32 = True; the exact-fp32 SIMT kernels of frame_mix.cu stay
+// for strict-fp32 runs.
+#include "common.cuh"
+#include "tc05.cuh"
+#include <atomic>
+
+namespace smow {
+
+constexpr int TC_M = 128;            // pixels per CTA tile = TMEM lanes
+constexpr int TC_KC = 32;            // channels per K chunk: 128 bytes = one swizzle row
+constexpr int TC_A_BYTES = TC_M * TC_KC * 4;
+constexpr int TC_MAX_STAGES = 4;
+
+// ------------------------------------------------------------------------------------------------ host: tensor maps
+EncodeTiledFn tensor_map_encoder() {
+  static std::atomic<EncodeTiledFn> cached{nullptr};
+  EncodeTiledFn fn = cached.load(std::memory_order_acquire);
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p ||
+      q != cudaDriverEntryPointSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  cached.store(fn, std::memory_order_release);
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return fail(SMOW_EINVAL, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t d[5], s[5];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  const CUtensorMapSwizzle sw = swizzle_bytes == SWIZZLE_128B_ATOM32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                              : swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SMOW_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ apply kernel
+struct MixTcParams {
+  int C, T, ntiles, shift, own_off;
+  int Nc;            // MMA N = output channels per CTA (multiple of 16, <= 256)
+  int kc;            // 32-channel K chunks per source frame
+  int stages;        // ring depth
+  int b_bytes;       // bytes of one B tile = Nc * 128
+  int tmem_cols;     // power of two >= max(32, Nc)
+  int out_cw;        // channels per output staging tile: 32 (128-byte swizzle) or 16 (64-byte swizzle)
+  const float* bias; // [T][C] or null
+};
+
+__global__ void __launch_bounds__(128)
+mix_apply_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
+                    const __grid_constant__ CUtensorMap tm_out, const MixTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], accum_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int rest = blockIdx.x;
+  const int f = rest % p.T;
+  rest /= p.T;
+  const int tile = rest % p.ntiles, b = rest / p.ntiles;
+  const int n0 = blockIdx.y * p.Nc;
+  const int stage_bytes = TC_A_BYTES + p.b_bytes;
+  const int total = 2 * p.kc;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_in);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_out);
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer: 2 sources x kc chunks through the ring
+    const int fsrc = (f + p.shift) % p.T, g = (f + p.own_off) % p.T;
+    for (int it = 0; it < total; ++it) {
+      const int s = it % p.stages;
+      if (it >= p.stages) mbar_wait_wd(&empty_bar[s], (uint32_t)((it / p.stages) - 1) & 1u);
+      const int src = it / p.kc, kk = it - src * p.kc;
+      uint8_t* a_dst = ring + (size_t)s * stage_bytes;
+      mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+      tma_load_3d(a_dst, &tm_in, kk * TC_KC, tile * TC_M, b * p.T + (src == 0 ? f : fsrc), &full_bar[s]);
+      tma_load_2d(a_dst + TC_A_BYTES, &tm_w, kk * TC_KC, (src == 0 ? 0 : (1 + g) * p.C) + n0, &full_bar[s]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer: one thread, K = 8 channels per instruction
+    const uint32_t idesc = umma_idesc_tf32(TC_M, p.Nc, 0, 0);
+    for (int it = 0; it < total; ++it) {
+      const int s = it % p.stages;
+      mbar_wait_wd(&full_bar[s], (uint32_t)(it / p.stages) & 1u);
+      tc_fence_after_sync();
+      const int kk = it % p.kc;
+      const int left = p.C - kk * TC_KC;                          // channels left in this source frame
+      const int ksteps = left >= TC_KC ? TC_KC / 8 : (left + 7) / 8;
+      const uint8_t* a_src = ring + (size_t)s * stage_bytes;
+      const uint64_t adesc = umma_desc_kmajor(a_src, 1024, 2), bdesc = umma_desc_kmajor(a_src + TC_A_BYTES, 1024, 2);
+      for (int k = 0; k < ksteps; ++k)                            // +32 bytes along K inside the swizzle atom: +2 in the address field
+        umma_tf32(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, it > 0 || k > 0);
+      umma_commit(&empty_bar[s]);                                 // stage free once these MMAs have read it
+    }
+    umma_commit(&accum_bar);                                      // accumulator complete
+  }
+  __syncwarp();
+
+  // ---- epilogue: TMEM -> registers (+ bias) -> swizzled shared-memory tile -> TMA store
+  mbar_wait_wd(&accum_bar, 0);
+  tc_fence_after_sync();
+  const int row = warp * 32 + lane;
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  const float* bias = p.bias ? p.bias + (size_t)f * p.C + n0 : nullptr;
+  for (int c = 0; c < p.Nc; c += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + (uint32_t)c, r);
+    tmem_ld_wait();
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n0 + c + j < p.C) v[j] += __ldg(bias + c + j);
+    }
+    uint8_t* base;
+    int j0, sw;
+    if (p.out_cw == 32) { base = ring + (size_t)(c >> 5) * TC_A_BYTES + row * 128; j0 = (c & 31) >> 2; sw = row & 7; }
+    else                { base = ring + row * 64; j0 = 0; sw = (row >> 1) & 3; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(base + (((j0 + q) ^ sw) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (p.out_cw == 32) {
+      for (int t = 0; t < p.Nc / 32; ++t)
+        tma_store_3d(&tm_out, ring + (size_t)t * TC_A_BYTES, n0 + 32 * t, tile * TC_M, b * p.T + f);
+    } else {
+      tma_store_3d(&tm_out, ring, n0, tile * TC_M, b * p.T + f);
+    }
+    bulk_commit();
+    bulk_wait_read0();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+  }
+}
+
+// tile plan for C channels; false when the channel count is not covered
+static bool tc_plan(int C, MixTcParams& p, int& nsplit) {
+  if (C < 16 || C > 512 || C % 4 != 0) return false;
+  const int cpad = (C + 15) / 16 * 16;                 // 28 -> 32
+  nsplit = cpad > 256 ? 2 : 1;                         // 320 -> 2 x 160, 512 -> 2 x 256
+  if (cpad % (16 * nsplit) != 0) return false;
+  p.Nc = cpad / nsplit;
+  p.out_cw = (p.Nc % 32 == 0) ? 32 : 16;
+  if (p.out_cw == 16 && p.Nc != 16) return false;      // 16, 28, and every multiple of 32 (x2 above 256)
+  p.kc = (C + TC_KC - 1) / TC_KC;
+  p.b_bytes = p.Nc * 128;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.Nc) p.tmem_cols *= 2;
+  const int stage_bytes = TC_A_BYTES + p.b_bytes;
+  p.stages = 2 * p.kc < TC_MAX_STAGES ? 2 * p.kc : TC_MAX_STAGES;
+  while (p.stages > 2 && (size_t)p.stages * stage_bytes + 2048 > 200 * 1024) --p.stages;
+  return true;
+}
+
+}  // namespace smow
+
+using namespace smow;
+
+extern "C" {
+
+int smow_frame_mix_tc_supported(int C, int T) {
+  MixTcParams p;
+  int nsplit;
+  return (tc_plan(C, p, nsplit) && (T == 2 || T == 4)) ? 1 : 0;
+}
+
+int smow_frame_mix_apply_tc(const float* in, const float* wpack, const float* bias, float* out, int B, int C, int T,
+                            int64_t hw, int64_t out_pitch, int shift, int own_off, void* stream) {
+  if (!in || !wpack || !out || B <= 0 || hw <= 0) return fail(SMOW_EINVAL, "frame_mix_tc: bad shape / null pointer");
+  if (!smow_frame_mix_tc_supported(C, T)) return fail(SMOW_EDTYPE, "frame_mix_tc: unsupported C = %d / T = %d", C, T);
+  if (out_pitch < C || out_pitch % 4 != 0) return fail(SMOW_EINVAL, "frame_mix_tc: out_pitch must be >= C and a multiple of 4");
+  if (!aligned16(in) || !aligned16(out) || !aligned16(wpack)) return fail(SMOW_EALIGN, "frame_mix_tc: 16 B alignment");
+  const int64_t ntiles = (hw + TC_M - 1) / TC_M;
+  if ((int64_t)B * T * ntiles > 0x7fffffffll || hw > 0x7fffffffll) return fail(SMOW_ERANGE, "frame_mix_tc: tensor too large");
+  MixTcParams p;
+  int nsplit = 1;
+  if (!tc_plan(C, p, nsplit)) return fail(SMOW_EDTYPE, "frame_mix_tc: unsupported C = %d", C);
+  p.C = C; p.T = T; p.ntiles = (int)ntiles; p.shift = ((shift % T) + T) % T; p.own_off = ((own_off % T) + T) % T;
+  p.bias = bias;
+  const int stage_bytes = TC_A_BYTES + p.b_bytes;
+  size_t smem = (size_t)p.stages * stage_bytes;
+  const size_t out_bytes = p.out_cw == 32 ? (size_t)(p.Nc / 32) * TC_A_BYTES : (size_t)TC_M * 64;
+  if (smem < out_bytes) smem = out_bytes;
+  smem += 1024;                                        // alignment slack for the 1024-byte swizzle atoms
+
+  CUtensorMap tm_in, tm_w, tm_out;
+  {
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)hw, (uint64_t)B * T};
+    const uint64_t str[2] = {(uint64_t)C * 4, (uint64_t)hw * C * 4};
+    const uint32_t box[3] = {TC_KC, TC_M, 1};
+    if (int rc = make_tensor_map(&tm_in, in, 3, dims, str, box, 128)) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)C, (uint64_t)(1 + T) * C};
+    const uint64_t str[1] = {(uint64_t)C * 4};
+    const uint32_t box[2] = {TC_KC, (uint32_t)p.Nc};
+    if (int rc = make_tensor_map(&tm_w, wpack, 2, dims, str, box, 128)) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)hw, (uint64_t)B * T};
+    const uint64_t str[2] = {(uint64_t)out_pitch * 4, (uint64_t)hw * out_pitch * 4};
+    const uint32_t box[3] = {(uint32_t)p.out_cw, TC_M, 1};
+    if (int rc = make_tensor_map(&tm_out, out, 3, dims, str, box, p.out_cw * 4)) return rc;
+  }
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(mix_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("frame_mix_tc (shared-memory opt-in)");
+  const dim3 grid((unsigned)((int64_t)B * T * ntiles), (unsigned)nsplit);
+  mix_apply_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(tm_in, tm_w, tm_out, p);
+  count_launch();
+  return check_launch("frame_mix_apply_tc");
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Weight gradients on the tensor cores.  For every (pair b, 64-pixel tile, frame f):
+//     D_0        += X_f^T            G_f          (-> dW_0, the shared matrix)
+//     D_{1+g(f)} += X_{(f+shift)%T}^T G_f          (-> dW_{1+g}, g = (f + own_off) % T)
+// with M = input channels, N = output channels, K = pixels.  The NDHWC tiles are exactly what TMA delivers
+// ([pixels][32 channels], 128-byte swizzle), and with the CHANNEL index contiguous they are "MN-major" operands for
+// both A and B: no transposition anywhere.  A CTA owns a range of (pair, tile) units, keeps its (1 + T) accumulators
+// [128 x Ncw] in tensor memory for the whole range and writes ONE partial per CTA; a second kernel adds the partials in
+// index order (deterministic).  M is always 128: for C < 128 the upper accumulator rows hold products of whatever
+// follows the tile in shared memory and are never read.
+// =====================================================================================================================
+namespace smow {
+
+constexpr int WG_PX = 64;                         // pixels per tile (K per stage; 8 MMAs of K = 8)
+constexpr int WG_BLK_BYTES = WG_PX * 128;         // one [64 px][32 ch] block = 8 KB
+constexpr int WG_MAX_STAGES = 4;
+
+struct WgradTcParams {
+  int C, T, shift, own_off;
+  int ntiles;          // 64-pixel tiles per frame
+  int nunits;          // B * ntiles
+  int units_per_cta;
+  int mblk;            // 32-channel blocks of the A operands loaded per step (<= 4)
+  int nblk;            // 32-channel blocks of the B operand = Ncw / 32 (Ncw = 32 * nblk, or 16 for C = 16)
+  int Ncw;             // MMA N
+  int stages, stage_bytes, tmem_cols;
+  int dbg;
+  float* part;         // [ctas][mchunks*nchunks ...] see below
+};
+
+// partial layout: part[((cta * (1+T) + slot) * C + ci) * C + co]
+__global__ void __launch_bounds__(128)
+mix_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, const WgradTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[WG_MAX_STAGES], empty_bar[WG_MAX_STAGES], accum_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.z * p.Ncw;      // channel offsets of this CTA's [128 x Ncw] block
+  const int u0 = blockIdx.x * p.units_per_cta;
+  int u1 = u0 + p.units_per_cta;
+  if (u1 > p.nunits) u1 = p.nunits;
+  const int steps = (u1 - u0) * p.T;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_g);
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int a_bytes = p.mblk * WG_BLK_BYTES;                     // one A operand (all its channel blocks)
+
+  if (warp == 0 && lane == 0) {
+    for (int it = 0; it < steps; ++it) {
+      const int s = it % p.stages;
+      if (it >= p.stages) mbar_wait_wd(&empty_bar[s], (uint32_t)((it / p.stages) - 1) & 1u);
+      const int u = u0 + it / p.T, f = it % p.T;
+      const int b = u / p.ntiles, tile = u - b * p.ntiles;
+      const int fs = (f + p.shift) % p.T;
+      uint8_t* dst = ring + (size_t)s * p.stage_bytes;
+      mbar_expect_tx(&full_bar[s], (uint32_t)((2 * p.mblk + p.nblk) * WG_BLK_BYTES));
+      for (int j = 0; j < p.mblk; ++j) {
+        tma_load_3d(dst + j * WG_BLK_BYTES, &tm_x, m0 + 32 * j, tile * WG_PX, b * p.T + f, &full_bar[s]);
+        tma_load_3d(dst + a_bytes + j * WG_BLK_BYTES, &tm_x, m0 + 32 * j, tile * WG_PX, b * p.T + fs, &full_bar[s]);
+      }
+      for (int j = 0; j < p.nblk; ++j)
+        tma_load_3d(dst + 2 * a_bytes + j * WG_BLK_BYTES, &tm_g, n0 + 32 * j, tile * WG_PX, b * p.T + f, &full_bar[s]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = umma_idesc_tf32(128, p.Ncw, 1, 1);
+    uint32_t started = 0;                                         // bit m set once accumulator m holds data
+    for (int it = 0; it < steps; ++it) {
+      const int s = it % p.stages;
+      mbar_wait_wd(&full_bar[s], (uint32_t)(it / p.stages) & 1u);
+      tc_fence_after_sync();
+      const int f = it % p.T, g = (f + p.own_off) % p.T;
+      const uint8_t* src = ring + (size_t)s * p.stage_bytes;
+      // MN-major TF32 operands exist in ONE shared-memory layout: 128-byte rows swizzled in 32-byte units (layout type 1,
+      // TMA mode 128B_ATOM_32B); its K atom is 4 pixel rows = 512 bytes (SBO), the next 32-channel block is LBO away
+      uint32_t lbo = WG_BLK_BYTES, sbo = (p.dbg & 16) ? 1024 : 512;
+      if (p.dbg & 1) { const uint32_t t = lbo; lbo = sbo; sbo = t; }
+      const uint64_t a1 = umma_desc_mnmajor(src, lbo, sbo, 1);
+      const uint64_t a2 = umma_desc_mnmajor(src + a_bytes, lbo, sbo, 1);
+      const uint64_t bd = umma_desc_mnmajor(src + 2 * a_bytes, lbo, sbo, 1);
+      const uint32_t d0 = tmem, dg = tmem + (uint32_t)((1 + g) * p.Ncw);
+      for (int k = 0; k < WG_PX / 8; ++k) {                       // 8 pixels = one 1024-byte swizzle atom per step: +64
+        umma_tf32(d0, a1 + 64 * k, bd + 64 * k, idesc, (started & 1u) || k > 0);
+        umma_tf32(dg, a2 + 64 * k, bd + 64 * k, idesc, ((started >> (1 + g)) & 1u) || k > 0);
+      }
+      started |= 1u | (1u << (1 + g));
+      umma_commit(&empty_bar[s]);
+    }
+    umma_commit(&accum_bar);
+  }
+  __syncwarp();
+
+  mbar_wait_wd(&accum_bar, 0);
+  tc_fence_after_sync();
+  const int ci = m0 + warp * 32 + lane;
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  const bool all = steps >= p.T;                                   // every accumulator was written at least once
+  for (int m = 0; m <= p.T; ++m) {
+    float* dst = p.part + (((size_t)blockIdx.x * (1 + p.T) + m) * p.C + ci) * p.C + n0;
+    for (int c = 0; c < p.Ncw; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr + (uint32_t)(m * p.Ncw + c), r);
+      tmem_ld_wait();
+      if (ci < p.C) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (n0 + c + 4 * q < p.C)
+            *reinterpret_cast<float4*>(dst + c + 4 * q) =
+                all ? make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                  __uint_as_float(r[4 * q + 3]))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+  }
+}
+
+// gw[m][ci][co] = sum over CTAs of part[cta][m][ci][co], in CTA order.  grid (ceil(C*C/256), 1+T), block 256.
+__global__ void __launch_bounds__(256)
+mix_wgrad_tc_combine_kernel(const float* __restrict__ part, float* __restrict__ gw, int CC, int nm, int nctas) {
+  const int e = blockIdx.x * 256 + threadIdx.x, m = blockIdx.y;
+  if (e >= CC) return;
+  const float* src = part + (size_t)m * CC + e;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  int c = 0;
+  for (; c + 4 <= nctas; c += 4) {
+    t0 += src[(size_t)(c + 0) * nm * CC];
+    t1 += src[(size_t)(c + 1) * nm * CC];
+    t2 += src[(size_t)(c + 2) * nm * CC];
+    t3 += src[(size_t)(c + 3) * nm * CC];
+  }
+  for (; c < nctas; ++c) t0 += src[(size_t)c * nm * CC];
+  gw[(size_t)m * CC + e] = (t0 + t1) + (t2 + t3);
+}
+
+static bool wgrad_tc_plan(int B, int C, int T, int64_t hw, WgradTcParams& p, int& nctas, int& mchunks, int& nchunks) {
+  if (C < 16 || C > 512 || C % 4 != 0 || (T != 2 && T != 4)) return false;
+  if (C % 32 != 0 && C > 32) return false;                        // 16, 20, 24, 28, 32, then multiples of 32
+  p.C = C; p.T = T;
+  const int cblocks = (C + 31) / 32;
+  p.mblk = cblocks < 4 ? cblocks : 4;
+  mchunks = (cblocks + 3) / 4;
+  // accumulators: (1 + T) * Ncw columns <= 512
+  int ncw = 32 * cblocks;
+  const int cap = (512 / (1 + T)) / 32 * 32;                      // T = 4: 96 ; T = 2: 160
+  if (ncw > cap) ncw = cap;
+  while ((32 * cblocks) % ncw != 0) ncw -= 32;
+  if (C <= 16) ncw = 16;
+  p.Ncw = ncw;
+  p.nblk = (ncw + 31) / 32;
+  nchunks = C <= 16 ? 1 : (32 * cblocks) / ncw;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < (1 + T) * ncw) p.tmem_cols *= 2;
+  p.ntiles = (int)((hw + WG_PX - 1) / WG_PX);
+  p.nunits = B * p.ntiles;
+  int target = 2 * device_info().sms;
+  // the per-CTA partials must stay small next to the tensors themselves (<= 1/8 of x + gy)
+  const int64_t cap_ctas = ((int64_t)2 * B * T * hw * C) / ((int64_t)8 * (1 + T) * C * C);
+  if (cap_ctas < target) target = cap_ctas < 1 ? 1 : (int)cap_ctas;
+  nctas = p.nunits < target ? p.nunits : target;
+  p.units_per_cta = (p.nunits + nctas - 1) / nctas;
+  nctas = (p.nunits + p.units_per_cta - 1) / p.units_per_cta;
+  p.stage_bytes = (2 * p.mblk + p.nblk) * WG_BLK_BYTES;
+  p.stages = WG_MAX_STAGES;
+  while (p.stages > 2 && (size_t)p.stages * p.stage_bytes > 150 * 1024) --p.stages;
+  return true;
+}
+
+}  // namespace smow
+
+extern "C" {
+
+int64_t smow_frame_mix_wgrad_tc_workspace_bytes(int B, int C, int T, int64_t hw) {
+  WgradTcParams p;
+  int nctas, mch, nch;
+  if (B <= 0 || hw <= 0 || !wgrad_tc_plan(B, C, T, hw, p, nctas, mch, nch)) return 0;
+  return (int64_t)nctas * (1 + T) * C * C * (int64_t)sizeof(float);
+}
+
+int smow_frame_mix_wgrad_tc(const float* x, const float* gy, float* gw, int B, int C, int T, int64_t hw, int shift,
+                            int own_off, void* ws, int64_t ws_bytes, void* stream) {
+  if (!x || !gy || !gw || B <= 0 || hw <= 0) return fail(SMOW_EINVAL, "frame_mix_wgrad_tc: bad shape / null pointer");
+  WgradTcParams p;
+  int nctas, mch, nch;
+  if (!wgrad_tc_plan(B, C, T, hw, p, nctas, mch, nch)) return fail(SMOW_EDTYPE, "frame_mix_wgrad_tc: unsupported C = %d / T = %d", C, T);
+  if (!aligned16(x) || !aligned16(gy) || !aligned16(gw) || !ws || !aligned16(ws) ||
+      ws_bytes < smow_frame_mix_wgrad_tc_workspace_bytes(B, C, T, hw))
+    return fail(SMOW_EINVAL, "frame_mix_wgrad_tc: workspace of smow_frame_mix_wgrad_tc_workspace_bytes() bytes required");
+  p.shift = ((shift % T) + T) % T; p.own_off = ((own_off % T) + T) % T;
+  p.part = reinterpret_cast<float*>(ws);
+  p.dbg = option(OPT_TC_DEBUG);
+  CUtensorMap tm_x, tm_g;
+  const uint64_t dims[3] = {(uint64_t)C, (uint64_t)hw, (uint64_t)B * T};
+  const uint64_t str[2] = {(uint64_t)C * 4, (uint64_t)hw * C * 4};
+  const uint32_t box[3] = {32, WG_PX, 1};
+  if (int rc = make_tensor_map(&tm_x, x, 3, dims, str, box, SWIZZLE_128B_ATOM32)) return rc;
+  if (int rc = make_tensor_map(&tm_g, gy, 3, dims, str, box, SWIZZLE_128B_ATOM32)) return rc;
+  // M = 128 reads four 32-channel blocks from the A tile's base: pad the ring so that the read stays inside the allocation
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 4 * WG_BLK_BYTES + 1024;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(mix_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("frame_mix_wgrad_tc (shared-memory opt-in)");
+  cudaStream_t st = (cudaStream_t)stream;
+  mix_wgrad_tc_kernel<<<dim3(nctas, mch, nch), 128, smem, st>>>(tm_x, tm_g, p);
+  mix_wgrad_tc_combine_kernel<<<dim3((C * C + 255) / 256, 1 + T), 256, 0, st>>>(p.part, gw, C * C, 1 + T, nctas);
+  count_launch(2);
+  return check_launch("frame_mix_wgrad_tc");
+}
+
+}  // extern "C"

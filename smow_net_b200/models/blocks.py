@@ -122,22 +122,48 @@ class _CyclicMixGemm(torch.autograd.Function):
         return gX.view(B, T, H, W, Cin).permute(0, 4, 1, 2, 3), g_shared, gws[0], gws[1], gws[2], gws[3], gbias
 
 
-def cyclic_frame_mix(frames5d, shared, own):
-    """frames5d: (B,C,4,H,W); shared: module; own: list of 4 modules (own[k] acts on frame k)."""
-    if not (frames5d.is_cuda and frames5d.shape[2] == 4 and frames5d.dtype == torch.float32
-            and frames5d.is_contiguous(memory_format=torch.channels_last_3d)):
-        return _cyclic_frame_mix_composed(frames5d, shared, own)
+def tensor_core_mix_enabled():
+    """The tcgen05 frame-mix kernels compute TF32 products (fp32 accumulation): exactly what cuDNN does for the 1x1x1
+    convolutions they replace when torch.backends.cudnn.allow_tf32 is True (PyTorch's default) — so that flag decides.
+    With it off (strict fp32) the exact SIMT kernels / GEMMs run instead."""
+    return bool(torch.backends.cudnn.allow_tf32)
+
+
+def cyclic_frame_mix(frames5d, shared, own, shift=1, own_off=1):
+    """out[:, :, f] = shared(frames[f]) + own[(f + own_off) % T](frames[(f + shift) % T]),  T = len(own).
+
+    Decoder blocks (reference models/SMOW_Net.py:121-139): T = 4, shift = own_off = 1, own[k] acts on frame k.
+    Encoder temporal exchange (reference models/SMOW_Net.py:460-473): T = 2, shift = 1, own_off = 0,
+    own = [conv3d_time_3, conv3d_time_1]."""
+    T = len(own)
+    on_gpu = frames5d.is_cuda and frames5d.dim() == 5 and frames5d.shape[2] == T and frames5d.dtype == torch.float32
+    if not on_gpu:
+        return _frame_mix_composed(frames5d, shared, own, shift, own_off)
+    from .. import ops
+    c_out = shared.weight.shape[1] if isinstance(shared, nn.ConvTranspose3d) else shared.weight.shape[0]
     bias = None
     if shared.bias is not None:
-        # out[j] = shared(f_j) + own[j+1](f_{j+1}): frame j carries the shared bias plus the bias of own[(j+1) % 4]
-        bias = torch.stack([shared.bias + own[(j + 1) % 4].bias for j in range(4)])
+        # frame f carries the shared bias plus the bias of the own-conv that feeds it
+        bias = torch.stack([shared.bias + own[(f + own_off) % T].bias for f in range(T)])
+    if tensor_core_mix_enabled() and ops.frame_mix_tc_supported(frames5d, c_out, T):
+        # 1 + T matrices in the orientation the parameters are stored in: Conv3d (out, in) / ConvTranspose3d (in, out)
+        pack = torch.stack([m.weight[:, :, 0, 0, 0] for m in [shared] + list(own)])
+        return ops.frame_mix_tc(frames5d, pack, bias, T, shift, own_off, nk=not isinstance(shared, nn.ConvTranspose3d))
+    if T != 4 or shift != 1 or own_off != 1 or not frames5d.is_contiguous(memory_format=torch.channels_last_3d):
+        return _frame_mix_composed(frames5d, shared, own, shift, own_off)
     w_shared = _mix_matrix(shared)
-    from .. import ops
     if ops.frame_mix_supported(frames5d, w_shared.shape[1]):
-        # the large decoder levels (C = 16 / 28 / 32 / 64): one hand-written pass instead of five GEMM passes
+        # strict fp32, the large decoder levels (C = 16 / 28 / 32 / 64): exact SIMT kernels
         y = ops.frame_mix(frames5d, w_shared, torch.stack([_mix_matrix(m) for m in own]))
         return y if bias is None else y + bias.t().reshape(1, -1, 4, 1, 1)
     return _CyclicMixGemm.apply(frames5d, w_shared, *[_mix_matrix(m) for m in own], bias)
+
+
+def _frame_mix_composed(frames5d, shared, own, shift, own_off):
+    """The reference's composition, any T: slices, 1x1x1 convolutions, adds, concat."""
+    T = len(own)
+    parts = [frames5d[:, :, k:k + 1] for k in range(T)]
+    return torch.cat([shared(parts[f]) + own[(f + own_off) % T](parts[(f + shift) % T]) for f in range(T)], dim=2)
 
 
 def _identity_1x1(conv):

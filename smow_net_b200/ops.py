@@ -516,3 +516,88 @@ def frame_mix(x, w_shared, w_own):
     if w_shared.dtype != torch.float32 or w_own.dtype != torch.float32:
         raise RuntimeError("frame_mix: fp32 matrices only")
     return _FrameMix.apply(x, w_shared, w_own)
+
+
+# ----------------------------------------------------------------------------- N4 on tensor cores (tcgen05 / TMEM / TMA)
+def frame_mix_apply_bytes(B, C, T, hw, s=4):
+    """Algorithmic bytes of one apply pass: the T-frame tensor read once and written once."""
+    return 2 * B * T * C * hw * s
+
+
+def frame_mix_wgrad_bytes(B, C, T, hw, s=4):
+    """Weight gradients: x and gy are read once; the (1+T) C x C results are negligible."""
+    return 2 * B * T * C * hw * s + (1 + T) * C * C * 4
+
+
+def frame_mix_tc_supported(x, c_out, T):
+    """True when the tcgen05 kernels take this tensor: CUDA fp32 (B,C,T,H,W) channels_last_3d, C_in = C_out covered."""
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.shape[2] == T and x.shape[1] == c_out
+            and x.shape[0] > 0 and bool(_lib.load().smow_frame_mix_tc_supported(int(c_out), int(T))))
+
+
+class _FrameMixTC(torch.autograd.Function):
+    """out[:, :, f] = W_0 x[:, :, f] + W_{1+(f+own_off)%T} x[:, :, (f+shift)%T] (+ bias[f]) as a TMA-fed tcgen05 GEMM.
+
+    `pack` holds the 1+T matrices either as [m][out][in] (`nk=True`: Conv3d 1x1x1 weights as stored) or as [m][in][out]
+    (`nk=False`: ConvTranspose3d weights as stored); its gradient comes back in the same orientation."""
+
+    @staticmethod
+    def forward(ctx, x, pack, bias, T, shift, own_off, nk):
+        B, C, _, H, W = x.shape
+        x = x.contiguous(memory_format=torch.channels_last_3d)
+        pack = pack.contiguous()
+        w_nk = pack if nk else pack.transpose(1, 2).contiguous()          # [m][out][in] feeds the forward GEMM
+        y = torch.empty_like(x, memory_format=torch.channels_last_3d)
+        b = None if bias is None else bias.contiguous().float()
+        lib = _lib.load()
+        with torch.cuda.device_of(x):
+            _call("frame_mix_fwd", frame_mix_apply_bytes(B, C, T, H * W), lib.smow_frame_mix_apply_tc,
+                  x.data_ptr(), w_nk.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(), B, C, T, H * W, C,
+                  shift, own_off, _stream())
+        ctx.save_for_backward(x, pack)
+        ctx.cfg = (T, shift, own_off, nk, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, pack = ctx.saved_tensors
+        T, shift, own_off, nk, has_bias = ctx.cfg
+        B, C, _, H, W = x.shape
+        gy = gy.contiguous(memory_format=torch.channels_last_3d)
+        w_kn = pack.transpose(1, 2).contiguous() if nk else pack           # [m][in][out] feeds the d(input) GEMM
+        gx = torch.empty_like(x, memory_format=torch.channels_last_3d)
+        gpack = torch.empty_like(pack)
+        lib = _lib.load()
+        n = int(lib.smow_frame_mix_wgrad_tc_workspace_bytes(B, C, T, H * W))
+        ws = torch.empty(max(n, 16), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device_of(x):
+            # gX_k = W_0^T gY_k + W_{1+g}^T gY_{k-shift}: the same kernel on the transposed matrices
+            _call("frame_mix_bwd", frame_mix_apply_bytes(B, C, T, H * W), lib.smow_frame_mix_apply_tc,
+                  gy.data_ptr(), w_kn.data_ptr(), None, gx.data_ptr(), B, C, T, H * W, C,
+                  (T - shift) % T, (own_off - shift) % T, _stream())
+            if nk:      # gradient wanted as [m][out][in]: swap the operand roles (see include/smow_b200.h)
+                _call("frame_mix_wgrad", frame_mix_wgrad_bytes(B, C, T, H * W), lib.smow_frame_mix_wgrad_tc,
+                      gy.data_ptr(), x.data_ptr(), gpack.data_ptr(), B, C, T, H * W, (T - shift) % T, (own_off - shift) % T,
+                      ws.data_ptr(), n, _stream())
+            else:
+                _call("frame_mix_wgrad", frame_mix_wgrad_bytes(B, C, T, H * W), lib.smow_frame_mix_wgrad_tc,
+                      x.data_ptr(), gy.data_ptr(), gpack.data_ptr(), B, C, T, H * W, shift, own_off,
+                      ws.data_ptr(), n, _stream())
+        gbias = gy.sum(dim=(0, 3, 4)).t() if has_bias else None             # (T, C)
+        return gx, gpack, gbias, None, None, None, None
+
+
+def frame_mix_tc(x, pack, bias=None, T=4, shift=1, own_off=1, nk=True):
+    """Temporal frame mix on the 5th-generation tensor cores (TF32 products, fp32 accumulation).  x (B,C,T,H,W);
+    pack (1+T,C,C); bias (T,C) or None -> (B,C,T,H,W) channels_last_3d.  Decoder blocks: T=4, shift=1, own_off=1
+    (reference models/SMOW_Net.py:121-139); encoder temporal exchange: T=2, shift=1, own_off=0 (:460-473)."""
+    _require_cuda(x, pack, bias)
+    C = x.shape[1] if x.dim() == 5 else -1
+    if not frame_mix_tc_supported(x, C, T):
+        raise RuntimeError("frame_mix_tc: needs an fp32 CUDA (B,C,%d,H,W) stack with a covered channel count, got %s"
+                           % (T, tuple(x.shape)))
+    if tuple(pack.shape) != (1 + T, C, C) or pack.dtype != torch.float32:
+        raise RuntimeError("frame_mix_tc: pack must be fp32 (1+T,C,C)=%s, got %s %s" % ((1 + T, C, C), pack.dtype, tuple(pack.shape)))
+    if bias is not None and (tuple(bias.shape) != (T, C) or bias.dtype != torch.float32):
+        raise RuntimeError("frame_mix_tc: bias must be fp32 (T,C)")
+    return _FrameMixTC.apply(x, pack, bias, T, shift, own_off, nk)

@@ -68,12 +68,12 @@ def use_oracle_ops(monkeypatch):
     from smow_net_b200.models import blocks
     monkeypatch.setattr(ops, "semantic_tokens", torch_ref.ref_semantic_tokens)
 
-    def mix(frames5d, shared, own):
-        bias = None
+    def mix(frames5d, shared, own, shift=1, own_off=1):
+        T, bias = len(own), None
         if shared.bias is not None:
-            bias = torch.stack([shared.bias + own[(j + 1) % 4].bias for j in range(4)])
+            bias = torch.stack([shared.bias + own[(f + own_off) % T].bias for f in range(T)])
         return torch_ref.ref_cyclic_frame_mix(frames5d, blocks._mix_matrix(shared),
-                                              torch.stack([blocks._mix_matrix(m) for m in own]), bias)
+                                              torch.stack([blocks._mix_matrix(m) for m in own]), bias, shift, own_off)
     monkeypatch.setattr(blocks, "cyclic_frame_mix", mix)
 
 
