@@ -439,8 +439,10 @@ static bool wgrad_tc_plan(int B, int C, int T, int64_t hw, WgradTcParams& p, int
   p.ntiles = (int)((hw + WG_PX - 1) / WG_PX);
   p.nunits = B * p.ntiles;
   int target = 2 * device_info().sms;
-  // the per-CTA partials must stay small next to the tensors themselves (<= 1/8 of x + gy)
-  const int64_t cap_ctas = ((int64_t)2 * B * T * hw * C) / ((int64_t)8 * (1 + T) * C * C);
+  // the per-CTA partials must stay small next to the tensors themselves: <= 1/8 of x + gy, or 16 MB for small tensors
+  int64_t budget = ((int64_t)2 * B * T * hw * C * 4) / 8;
+  if (budget < (16ll << 20)) budget = 16ll << 20;
+  const int64_t cap_ctas = budget / ((int64_t)(1 + T) * C * C * 4);
   if (cap_ctas < target) target = cap_ctas < 1 ? 1 : (int)cap_ctas;
   nctas = p.nunits < target ? p.nunits : target;
   p.units_per_cta = (p.nunits + nctas - 1) / nctas;

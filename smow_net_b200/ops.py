@@ -100,12 +100,16 @@ class KernelTimer:
     """Collects CUDA-event timings of every C-ABI call made while active (bench.py roofline)."""
 
     def __init__(self):
-        self.records = []  # (name, algorithmic_bytes, start_event, end_event)
+        self.records = []  # (name, algorithmic_bytes, start_event, end_event, meta)
+
+    def calls(self):
+        """[(name, meta dict)] of every recorded C-ABI call, in launch order (smow_net_b200.probe replays them)."""
+        return [(r[0], r[4]) for r in self.records]
 
     def summary(self, by_shape=False):
         """Per operator totals; by_shape=True keeps launches of different sizes apart (key 'name@<bytes>')."""
         out = {}
-        for name, nbytes, e0, e1 in self.records:
+        for name, nbytes, e0, e1, _meta_ in self.records:
             ms = e0.elapsed_time(e1)
             s = out.setdefault("%s@%d" % (name, nbytes) if by_shape else name, {"calls": 0, "ms": 0.0, "bytes": 0})
             s["calls"] += 1
@@ -129,16 +133,28 @@ def kernel_timer():
         _TIMER = prev
 
 
+_NEXT_META = None
+
+
+def _meta(**kw):
+    """Shape / layout of the next C-ABI call, kept only while a kernel_timer is active."""
+    global _NEXT_META
+    if _TIMER is not None:
+        _NEXT_META = kw
+
+
 def _call(name, nbytes, fn, *args):
+    global _NEXT_META
     if _TIMER is None:
         _lib.check(fn(*args), name)
         return
+    meta, _NEXT_META = _NEXT_META, None
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     _lib.check(fn(*args), name)
     e1.record()
-    _TIMER.records.append((name, nbytes, e0, e1))
+    _TIMER.records.append((name, nbytes, e0, e1, meta))
 
 
 # algorithmic bytes per launch (SURVEY §8(d)); s = bytes per feature element, flow is fp32
@@ -151,7 +167,13 @@ def warp_bwd_bytes(B, C, H, W, s):
 
 
 def tlerp_fwd_bytes(B, Cd, Cs, hw, s):
-    return B * (6 * Cs * hw * s + 8 * Cd * hw * s)
+    """read 2*Cs*hw*s, write 4*Cs*hw*s.  The copy of the decoder half is NOT algorithmic."""
+    return B * 6 * Cs * hw * s
+
+
+def tlerp_fwd_overhead_bytes(B, Cd, hw, s):
+    """Extra traffic of the same launch when it also copies the decoder half into the concat buffer (read + write)."""
+    return B * 8 * Cd * hw * s
 
 
 def tlerp_bwd_bytes(B, Cs, hw, s):
@@ -197,6 +219,7 @@ class _WarpStack(torch.autograd.Function):
         xs, ys = base_grid(W, x.device), base_grid(H, x.device)
         lib = _lib.load()
         with torch.cuda.device_of(x):
+            _meta(B=B, C=C, H=H, W=W, dtype=_dtype_code(x), layout=layout, pair=0)
             _call("warp_stack_fwd", warp_fwd_bytes(B, C, H, W, x.element_size()), lib.smow_warp_stack_fwd,
                   x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(), out.data_ptr(),
                   B, C, H, W, _dtype_code(x), layout, _stream())
@@ -215,6 +238,7 @@ class _WarpStack(torch.autograd.Function):
         lib = _lib.load()
         ws, ws_bytes = _bwd_workspace(lib, x, ctx.layout, B, H, W)
         with torch.cuda.device_of(x):
+            _meta(B=B, C=C, H=H, W=W, dtype=_dtype_code(x), layout=ctx.layout, pair=0)
             _call("warp_stack_bwd", warp_bwd_bytes(B, C, H, W, x.element_size()), lib.smow_warp_stack_bwd,
                   gout.data_ptr(), x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),
                   gx.data_ptr(), gflow.data_ptr(), B, C, H, W, _dtype_code(x), ctx.layout,
@@ -238,6 +262,7 @@ class _WarpPair(torch.autograd.Function):
         xs, ys = base_grid(W, x1.device), base_grid(H, x1.device)
         lib = _lib.load()
         with torch.cuda.device_of(x1):
+            _meta(B=B, C=C, H=H, W=W, dtype=_dtype_code(x1), layout=layout, pair=1)
             _call("warp_stack_fwd", warp_fwd_bytes(B, C, H, W, x1.element_size()), lib.smow_warp_pair_fwd,
                   x1.data_ptr(), x2.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(), out.data_ptr(),
                   B, C, H, W, _dtype_code(x1), layout, _stream())
@@ -257,6 +282,7 @@ class _WarpPair(torch.autograd.Function):
         lib = _lib.load()
         with torch.cuda.device_of(x1):
             ws, ws_bytes = _bwd_workspace(lib, x1, ctx.layout, B, H, W)
+            _meta(B=B, C=C, H=H, W=W, dtype=_dtype_code(x1), layout=ctx.layout, pair=1)
             _call("warp_stack_bwd", warp_bwd_bytes(B, C, H, W, x1.element_size()), lib.smow_warp_pair_bwd,
                   gout.data_ptr(), x1.data_ptr(), x2.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),
                   g1.data_ptr(), g2.data_ptr(), gflow.data_ptr(), B, C, H, W, _dtype_code(x1), ctx.layout,
@@ -308,6 +334,7 @@ class _TLerpCat(torch.autograd.Function):
         cat = _empty((B, Cd + Cs, 4, h, w), skip, layout)
         lib = _lib.load()
         with torch.cuda.device_of(skip):
+            _meta(B=B, Cd=Cd, Cs=Cs, hw=h * w, dtype=_dtype_code(skip), layout=layout, pair=0)
             _call("tlerp_cat_fwd", tlerp_fwd_bytes(B, Cd, Cs, h * w, skip.element_size()), lib.smow_tlerp_cat_fwd,
                   dec.data_ptr() if dec is not None else None, skip.data_ptr(), cat.data_ptr(),
                   B, Cd, Cs, h * w, _dtype_code(skip), layout, _stream())
@@ -322,6 +349,7 @@ class _TLerpCat(torch.autograd.Function):
         gskip = _empty((B, Cs, 2, h, w), gcat, ctx.layout)
         lib = _lib.load()
         with torch.cuda.device_of(gcat):
+            _meta(B=B, Cd=Cd, Cs=Cs, hw=h * w, dtype=_dtype_code(gcat), layout=ctx.layout, pair=0)
             _call("tlerp_cat_bwd", tlerp_bwd_bytes(B, Cs, h * w, gcat.element_size()), lib.smow_tlerp_cat_bwd,
                   gcat.data_ptr(), gskip.data_ptr(), B, Cd, Cs, h * w, _dtype_code(gcat), ctx.layout, _stream())
         gdec = gcat[:, :Cd] if Cd > 0 else None  # strided view, as torch.cat's backward returns
@@ -350,6 +378,7 @@ class _TLerpPairCat(torch.autograd.Function):
         cat = _empty((B, Cd + Cs, 4, h, w), a, layout)
         lib = _lib.load()
         with torch.cuda.device_of(a):
+            _meta(B=B, Cd=Cd, Cs=Cs, hw=h * w, dtype=_dtype_code(a), layout=layout, pair=1)
             _call("tlerp_cat_fwd", tlerp_fwd_bytes(B, Cd, Cs, h * w, a.element_size()), lib.smow_tlerp_pair_cat_fwd,
                   dec.data_ptr() if dec is not None else None, a.data_ptr(), b.data_ptr(), cat.data_ptr(),
                   B, Cd, Cs, h * w, _dtype_code(a), layout, _stream())
@@ -365,6 +394,7 @@ class _TLerpPairCat(torch.autograd.Function):
         gb = _empty((B, Cs, h, w), gcat, ctx.layout)
         lib = _lib.load()
         with torch.cuda.device_of(gcat):
+            _meta(B=B, Cd=Cd, Cs=Cs, hw=h * w, dtype=_dtype_code(gcat), layout=ctx.layout, pair=1)
             _call("tlerp_cat_bwd", tlerp_bwd_bytes(B, Cs, h * w, gcat.element_size()), lib.smow_tlerp_pair_cat_bwd,
                   gcat.data_ptr(), ga.data_ptr(), gb.data_ptr(), B, Cd, Cs, h * w, _dtype_code(gcat),
                   ctx.layout, _stream())
@@ -417,6 +447,7 @@ class _SemanticTokens(torch.autograd.Function):
         n = int(lib.smow_tokenizer_workspace_bytes(B, C, H * W))
         ws = torch.empty(n, dtype=torch.uint8, device=x.device)
         with torch.cuda.device_of(x):
+            _meta(B=B, C=C, hw=H * W)
             _call("tokenizer_fwd", tokenizer_fwd_bytes(B, C, H * W), lib.smow_tokenizer_fwd,
                   x.data_ptr(), wa.data_ptr(), ba.data_ptr(), tokens.data_ptr(), stats.data_ptr(), B, C, H * W,
                   _lib.F32, _lib.NDHWC, ws.data_ptr(), n, _stream())
@@ -435,6 +466,7 @@ class _SemanticTokens(torch.autograd.Function):
         n = int(lib.smow_tokenizer_workspace_bytes(B, C, H * W))
         ws = torch.empty(n, dtype=torch.uint8, device=x.device)
         with torch.cuda.device_of(x):
+            _meta(B=B, C=C, hw=H * W)
             _call("tokenizer_bwd", tokenizer_bwd_bytes(B, C, H * W), lib.smow_tokenizer_bwd,
                   gtokens.data_ptr(), x.data_ptr(), wa.data_ptr(), ba.data_ptr(), tokens.data_ptr(), stats.data_ptr(),
                   gx.data_ptr(), gwa.data_ptr(), gba.data_ptr(), B, C, H * W, _lib.F32, _lib.NDHWC,
@@ -473,6 +505,7 @@ class _FrameMix(torch.autograd.Function):
         y = torch.empty_like(x, memory_format=torch.channels_last_3d)
         lib = _lib.load()
         with torch.cuda.device_of(x):
+            _meta(B=B, C=C, T=4, hw=H * W, tc=0)
             _call("frame_mix_fwd", frame_mix_bytes(B, C, H * W), lib.smow_frame_mix_apply,
                   x.data_ptr(), m0.data_ptr(), m1.data_ptr(), y.data_ptr(), B, C, H * W, 1, 1, _stream())
         ctx.save_for_backward(x, m0, m1)
@@ -490,9 +523,11 @@ class _FrameMix(torch.autograd.Function):
         n = int(lib.smow_frame_mix_wgrad_workspace_bytes(B, C, H * W))
         ws = torch.empty(n, dtype=torch.uint8, device=x.device)
         with torch.cuda.device_of(x):
+            _meta(B=B, C=C, T=4, hw=H * W, tc=0)
             _call("frame_mix_bwd", frame_mix_bytes(B, C, H * W), lib.smow_frame_mix_apply,
                   gy.data_ptr(), m0t.data_ptr(), m1t.data_ptr(), gx.data_ptr(), B, C, H * W, 3, 0, _stream())
-            _call("frame_mix_wgrad", frame_mix_bytes(B, C, H * W), lib.smow_frame_mix_wgrad,
+            _meta(B=B, C=C, T=4, hw=H * W, tc=0)
+            _call("frame_mix_wgrad", frame_mix_wgrad_bytes(B, C, 4, H * W), lib.smow_frame_mix_wgrad,
                   x.data_ptr(), gy.data_ptr(), gw.data_ptr(), B, C, H * W, ws.data_ptr(), n, _stream())
         return gx, gw[0], gw[1:]
 
@@ -551,6 +586,7 @@ class _FrameMixTC(torch.autograd.Function):
         b = None if bias is None else bias.contiguous().float()
         lib = _lib.load()
         with torch.cuda.device_of(x):
+            _meta(B=B, C=C, T=T, hw=H * W, tc=1)
             _call("frame_mix_fwd", frame_mix_apply_bytes(B, C, T, H * W), lib.smow_frame_mix_apply_tc,
                   x.data_ptr(), w_nk.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(), B, C, T, H * W, C,
                   shift, own_off, _stream())
@@ -572,14 +608,17 @@ class _FrameMixTC(torch.autograd.Function):
         ws = torch.empty(max(n, 16), dtype=torch.uint8, device=x.device)
         with torch.cuda.device_of(x):
             # gX_k = W_0^T gY_k + W_{1+g}^T gY_{k-shift}: the same kernel on the transposed matrices
+            _meta(B=B, C=C, T=T, hw=H * W, tc=1)
             _call("frame_mix_bwd", frame_mix_apply_bytes(B, C, T, H * W), lib.smow_frame_mix_apply_tc,
                   gy.data_ptr(), w_kn.data_ptr(), None, gx.data_ptr(), B, C, T, H * W, C,
                   (T - shift) % T, (own_off - shift) % T, _stream())
             if nk:      # gradient wanted as [m][out][in]: swap the operand roles (see include/smow_b200.h)
+                _meta(B=B, C=C, T=T, hw=H * W, tc=1)
                 _call("frame_mix_wgrad", frame_mix_wgrad_bytes(B, C, T, H * W), lib.smow_frame_mix_wgrad_tc,
                       gy.data_ptr(), x.data_ptr(), gpack.data_ptr(), B, C, T, H * W, (T - shift) % T, (own_off - shift) % T,
                       ws.data_ptr(), n, _stream())
             else:
+                _meta(B=B, C=C, T=T, hw=H * W, tc=1)
                 _call("frame_mix_wgrad", frame_mix_wgrad_bytes(B, C, T, H * W), lib.smow_frame_mix_wgrad_tc,
                       x.data_ptr(), gy.data_ptr(), gpack.data_ptr(), B, C, T, H * W, shift, own_off,
                       ws.data_ptr(), n, _stream())

@@ -77,8 +77,8 @@ def test_product_never_imports_the_oracle():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """bench.py --impl reference (the reference-port model on the host CPU) prints one JSON line with the contract's keys;
-    a small batch keeps it to a few seconds."""
+    """bench.py --impl reference (the reference's own modules from oracle/_ref/reference.zip on the host CPU; the oracle's
+    port only where that archive is absent) prints ONE JSON line with the contract's keys; a small batch keeps it short."""
     import json
     import subprocess
     import sys
@@ -91,7 +91,10 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["value"] > 0
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_runtime
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_runtime.available() else "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["nproc"] >= 1 and d["cpu_baseline"]["cpu_model"]
+    assert len([l for l in r.stdout.splitlines() if l.strip()]) == 1      # stdout is exactly the one JSON line
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
