@@ -351,7 +351,13 @@ def sweep_block(device):
                     for sigma in (0.3, 8.0):
                         meta = {"B": B, "C": C, "H": H, "W": H, "dtype": dt, "layout": lay, "pair": 0}
                         for op, ai in (("warp_stack_fwd", 0), ("warp_stack_bwd", 1)):
-                            t = probe.time_call(op, meta, device, footprint=1 << 30, max_sets=4, sigma=sigma)
+                            try:
+                                t = probe.time_call(op, meta, device, footprint=1 << 30, max_sets=4, sigma=sigma)
+                            except RuntimeError as e:               # a (dtype, layout) combination the library refuses
+                                rows.append({"op": op, "C": C, "H": H, "B": B, "dtype": "f32" if dt == _lib.F32 else "bf16",
+                                             "layout": "NDHWC" if lay == _lib.NDHWC else "NCDHW", "sigma": sigma,
+                                             "unsupported": str(e).splitlines()[0][:160]})
+                                continue
                             rows.append({"op": op, "C": C, "H": H, "B": B, "dtype": "f32" if dt == _lib.F32 else "bf16",
                                          "layout": "NDHWC" if lay == _lib.NDHWC else "NCDHW", "sigma": sigma,
                                          "ms": t["cold_ms"], "GB_per_s": t["bytes"] / t["cold_ms"] / 1e6,
@@ -361,7 +367,8 @@ def sweep_block(device):
     clk = clocks.stop()
 
     def best(op, dtype, layout, sigma):
-        r = [x["frac"] for x in rows if x["op"] == op and x["dtype"] == dtype and x["layout"] == layout and x["sigma"] == sigma]
+        r = [x["frac"] for x in rows if x["op"] == op and x["dtype"] == dtype and x["layout"] == layout and x["sigma"] == sigma
+             and "frac" in x]
         return {"min_frac": min(r), "max_frac": max(r)} if r else None
     return {"workload": "BASELINE.json configs[4]: warp+stack fwd / bwd, C x (H=W) in {64,128,256}^2, fp32 + bf16, NDHWC + NCDHW, "
                         "flow sigma 0.3 (init-like) and 8 (stress); B such that one launch moves >= 1 GiB; CUDA-graph replays "

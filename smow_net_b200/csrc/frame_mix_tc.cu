@@ -188,6 +188,146 @@ mix_apply_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent apply kernel
+// C <= 64 (the decoder levels that carry the bytes): the 1 + T weight matrices stay resident in shared memory, CTAs are
+// persistent and warp-specialised — warp 0 feeds the A ring by TMA, warp 1 issues tcgen05.mma into one of TWO
+// accumulators in tensor memory, warps 2-5 drain the other one (tcgen05.ld -> bias -> swizzled staging tile -> TMA
+// store, double-buffered) — so loads, tensor-core work and the epilogue of consecutive tiles overlap.
+constexpr int TCP_THREADS = 192;
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TCP_THREADS)
+mix_apply_tcp_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
+                     const __grid_constant__ CUtensorMap tm_out, const MixTcParams p, const int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], w_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int w_tile = p.Nc * 128;                                   // one (matrix, K chunk) weight tile
+  const int w_bytes = (1 + p.T) * p.kc * w_tile;
+  const int out_bytes = p.out_cw == 32 ? (p.Nc / 32) * TC_A_BYTES : TC_M * 64;
+  uint8_t* wsm = base;
+  uint8_t* ring = base + ((w_bytes + 1023) & ~1023);
+  uint8_t* stg = ring + (size_t)p.stages * TC_A_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = 2 * p.kc;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+    mbar_init(&w_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_in);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_out);
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---- producer: weights once, then the A tiles of every tile of this CTA
+    mbar_expect_tx(&w_bar, (uint32_t)w_bytes);
+    for (int m = 0; m <= p.T; ++m)
+      for (int kk = 0; kk < p.kc; ++kk)
+        tma_load_2d(wsm + (size_t)(m * p.kc + kk) * w_tile, &tm_w, kk * TC_KC, m * p.C, &w_bar);
+    int cnt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int f = t % p.T, rest = t / p.T, tile = rest % p.ntiles, b = rest / p.ntiles;
+      const int fsrc = (f + p.shift) % p.T;
+      for (int c = 0; c < chunks; ++c, ++cnt) {
+        const int s = cnt % p.stages;
+        if (cnt >= p.stages) mbar_wait_wd(&empty_bar[s], (uint32_t)((cnt / p.stages) - 1) & 1u);
+        const int src = c / p.kc, kk = c - src * p.kc;
+        mbar_expect_tx(&full_bar[s], TC_A_BYTES);
+        tma_load_3d(ring + (size_t)s * TC_A_BYTES, &tm_in, kk * TC_KC, tile * TC_M, b * p.T + (src == 0 ? f : fsrc), &full_bar[s]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer
+    const uint32_t idesc = umma_idesc_tf32(TC_M, p.Nc, 0, 0);
+    mbar_wait_wd(&w_bar, 0);
+    int cnt = 0, i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const int f = t % p.T, g = (f + p.own_off) % p.T, acc = i & 1;
+      mbar_wait_wd(&tempty_bar[acc], (uint32_t)((i >> 1) & 1) ^ 1u);       // the epilogue has drained this accumulator
+      tc_fence_after_sync();
+      const uint32_t d = tmem + (uint32_t)(acc * p.Nc);
+      for (int c = 0; c < chunks; ++c, ++cnt) {
+        const int s = cnt % p.stages;
+        mbar_wait_wd(&full_bar[s], (uint32_t)(cnt / p.stages) & 1u);
+        tc_fence_after_sync();
+        const int src = c / p.kc, kk = c - src * p.kc;
+        const int left = p.C - kk * TC_KC;
+        const int ksteps = left >= TC_KC ? TC_KC / 8 : (left + 7) / 8;
+        const uint64_t adesc = umma_desc_kmajor(ring + (size_t)s * TC_A_BYTES, 1024, 2);
+        const uint64_t bdesc = umma_desc_kmajor(wsm + (size_t)((src == 0 ? 0 : 1 + g) * p.kc + kk) * w_tile, 1024, 2);
+        for (int k = 0; k < ksteps; ++k) umma_tf32(d, adesc + 2 * k, bdesc + 2 * k, idesc, c > 0 || k > 0);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tfull_bar[acc]);
+    }
+  } else if (warp >= 2) {
+    // ---- epilogue warps: TMEM lane quadrant = warp % 4
+    const int q = warp & 3, row = q * 32 + lane;
+    const bool leader = threadIdx.x == 64;
+    int i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const int f = t % p.T, rest = t / p.T, tile = rest % p.ntiles, b = rest / p.ntiles, acc = i & 1;
+      uint8_t* sb = stg + (size_t)(i & 1) * out_bytes;
+      mbar_wait_wd(&tfull_bar[acc], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after_sync();
+      if (leader) bulk_wait_read1();                                        // the store that used this staging buffer is done
+      epi_bar_sync();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Nc);
+      const float* bias = p.bias ? p.bias + (size_t)f * p.C : nullptr;
+      for (int c = 0; c < p.Nc; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c + j < p.C) v[j] += __ldg(bias + c + j);
+        }
+        uint8_t* dst;
+        int j0, sw;
+        if (p.out_cw == 32) { dst = sb + (size_t)(c >> 5) * TC_A_BYTES + row * 128; j0 = (c & 31) >> 2; sw = row & 7; }
+        else                { dst = sb + row * 64; j0 = 0; sw = (row >> 1) & 3; }
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq)
+          *reinterpret_cast<float4*>(dst + (((j0 + qq) ^ sw) << 4)) = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&tempty_bar[acc]);                                        // accumulator free for the MMA warp
+      fence_proxy_async();
+      epi_bar_sync();
+      if (leader) {
+        if (p.out_cw == 32) {
+          for (int k = 0; k < p.Nc / 32; ++k) tma_store_3d(&tm_out, sb + (size_t)k * TC_A_BYTES, 32 * k, tile * TC_M, b * p.T + f);
+        } else {
+          tma_store_3d(&tm_out, sb, 0, tile * TC_M, b * p.T + f);
+        }
+        bulk_commit();
+      }
+    }
+    if (leader) bulk_wait_read0();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+  }
+}
+
 // tile plan for C channels; false when the channel count is not covered
 static bool tc_plan(int C, MixTcParams& p, int& nsplit) {
   if (C < 16 || C > 512 || C % 4 != 0) return false;
@@ -260,7 +400,32 @@ int smow_frame_mix_apply_tc(const float* in, const float* wpack, const float* bi
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(mix_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("frame_mix_tc (shared-memory opt-in)");
-  const dim3 grid((unsigned)((int64_t)B * T * ntiles), (unsigned)nsplit);
+  const int64_t total_tiles = (int64_t)B * T * ntiles;
+  if (p.kc <= 2 && nsplit == 1 && !(option(OPT_TC_DEBUG) & 32)) {
+    // persistent, warp-specialised variant with resident weights
+    const int w_bytes = ((1 + T) * p.kc * p.Nc * 128 + 1023) & ~1023;
+    const int out_b = p.out_cw == 32 ? (p.Nc / 32) * TC_A_BYTES : TC_M * 64;
+    const int fixed = w_bytes + 2 * out_b + 1024;
+    int stages = (110 * 1024 - fixed) / TC_A_BYTES;                 // two CTAs per SM when the weights allow it
+    int per_sm = 2;
+    if (stages < 3) { stages = (220 * 1024 - fixed) / TC_A_BYTES; per_sm = 1; }
+    if (stages > 8) stages = 8;
+    if (stages < 2) return fail(SMOW_EDTYPE, "frame_mix_tc: shared memory plan failed for C = %d", C);
+    MixTcParams pp = p;
+    pp.stages = stages;
+    pp.tmem_cols = 32;
+    while (pp.tmem_cols < 2 * p.Nc) pp.tmem_cols *= 2;
+    const size_t psmem = (size_t)fixed + (size_t)stages * TC_A_BYTES;
+    if (psmem > 48 * 1024 &&
+        cudaFuncSetAttribute(mix_apply_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem) != cudaSuccess)
+      return check_launch("frame_mix_tc (shared-memory opt-in)");
+    int64_t nctas = (int64_t)device_info().sms * per_sm;
+    if (nctas > total_tiles) nctas = total_tiles;
+    mix_apply_tcp_kernel<<<(unsigned)nctas, TCP_THREADS, psmem, (cudaStream_t)stream>>>(tm_in, tm_w, tm_out, pp, (int)total_tiles);
+    count_launch();
+    return check_launch("frame_mix_apply_tc");
+  }
+  const dim3 grid((unsigned)total_tiles, (unsigned)nsplit);
   mix_apply_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(tm_in, tm_w, tm_out, p);
   count_launch();
   return check_launch("frame_mix_apply_tc");
@@ -418,6 +583,132 @@ mix_wgrad_tc_combine_kernel(const float* __restrict__ part, float* __restrict__ 
   gw[(size_t)m * CC + e] = (t0 + t1) + (t2 + t3);
 }
 
+// ---- T = 4, C <= 32 (the big decoder levels): the four frames of a 64-pixel tile are stacked along M ---------------------
+// A = [X_0 ; X_1 ; X_2 ; X_3] (4 x 32 channel rows = the full M = 128; the four tiles sit 8 KB apart, which is exactly the
+// descriptor's MN-block stride), B = G_f:  D_f[f'*32 + ci, co] = sum_p X_f'[p, ci] G_f[p, co]  for all f' in ONE instruction
+// stream per f.  Needed blocks: f' = f (-> dW_0) and f' = (f + shift) % 4 (-> dW_{1+g}); every tile is loaded exactly once.
+constexpr int WG4_STAGE_BYTES = 8 * WG_BLK_BYTES;        // X_0..3, G_0..3
+constexpr int WG4_STAGES = 3;
+
+struct Wgrad4Params {
+  int C, shift, own_off, ntiles, nunits, Ncw;
+  float* part;                                           // [cta][8 slots][C][C]: slots 0..3 dW_0 from frame w, 4..7 dW_{1+g}
+};
+
+__global__ void __launch_bounds__(128)
+mix_wgrad_tc4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g, const Wgrad4Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[WG4_STAGES], empty_bar[WG4_STAGES], accum_bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tmem_cols = 4 * p.Ncw < 32 ? 32 : 4 * p.Ncw;            // 64 or 128
+  int nmine = 0;
+  for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) ++nmine;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG4_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&accum_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_g);
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    int it = 0;
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
+      const int s = it % WG4_STAGES;
+      if (it >= WG4_STAGES) mbar_wait_wd(&empty_bar[s], (uint32_t)((it / WG4_STAGES) - 1) & 1u);
+      const int b = u / p.ntiles, tile = u - b * p.ntiles;
+      uint8_t* dst = ring + (size_t)s * WG4_STAGE_BYTES;
+      mbar_expect_tx(&full_bar[s], WG4_STAGE_BYTES);
+      for (int f = 0; f < 4; ++f) {
+        tma_load_3d(dst + f * WG_BLK_BYTES, &tm_x, 0, tile * WG_PX, b * 4 + f, &full_bar[s]);
+        tma_load_3d(dst + (4 + f) * WG_BLK_BYTES, &tm_g, 0, tile * WG_PX, b * 4 + f, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = umma_idesc_tf32(128, p.Ncw, 1, 1);
+    for (int it = 0; it < nmine; ++it) {
+      const int s = it % WG4_STAGES;
+      mbar_wait_wd(&full_bar[s], (uint32_t)(it / WG4_STAGES) & 1u);
+      tc_fence_after_sync();
+      const uint8_t* src = ring + (size_t)s * WG4_STAGE_BYTES;
+      const uint64_t ad = umma_desc_mnmajor(src, WG_BLK_BYTES, 512, 1);
+      for (int f = 0; f < 4; ++f) {
+        const uint64_t bd = umma_desc_mnmajor(src + (4 + f) * WG_BLK_BYTES, WG_BLK_BYTES, 512, 1);
+        const uint32_t d = tmem + (uint32_t)(f * p.Ncw);
+        for (int k = 0; k < WG_PX / 8; ++k) umma_tf32(d, ad + 64 * k, bd + 64 * k, idesc, it > 0 || k > 0);
+      }
+      umma_commit(&empty_bar[s]);
+    }
+    umma_commit(&accum_bar);
+  }
+  __syncwarp();
+
+  mbar_wait_wd(&accum_bar, 0);
+  tc_fence_after_sync();
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  const int ci = lane;
+  const int f_own = (warp - p.shift + 4) & 3, g = (f_own + p.own_off) & 3;
+  for (int half = 0; half < 2; ++half) {
+    const int fsel = half == 0 ? warp : f_own, slot = half == 0 ? warp : 4 + g;
+    float* dst = p.part + (((size_t)blockIdx.x * 8 + slot) * p.C + ci) * p.C;
+    for (int c = 0; c < p.Ncw; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(taddr + (uint32_t)(fsel * p.Ncw + c), r);
+      tmem_ld_wait();
+      if (ci < p.C) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c + 4 * q < p.C)
+            *reinterpret_cast<float4*>(dst + c + 4 * q) =
+                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                            __uint_as_float(r[4 * q + 3]));
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, (uint32_t)tmem_cols);
+  }
+}
+
+// gw[0] = sum over CTAs and slots 0..3; gw[1+g] = sum over CTAs of slot 4+g.  grid (ceil(C*C/256), 5), block 256.
+__global__ void __launch_bounds__(256)
+mix_wgrad_tc4_combine_kernel(const float* __restrict__ part, float* __restrict__ gw, int CC, int nctas) {
+  const int e = blockIdx.x * 256 + threadIdx.x, m = blockIdx.y;
+  if (e >= CC) return;
+  float t0 = 0.f, t1 = 0.f;
+  if (m == 0) {
+    for (int c = 0; c < nctas; ++c) {
+      const float* src = part + (size_t)c * 8 * CC + e;
+      t0 += src[0] + src[(size_t)CC];
+      t1 += src[(size_t)2 * CC] + src[(size_t)3 * CC];
+    }
+  } else {
+    const float* src = part + (size_t)(3 + m) * CC + e;
+    int c = 0;
+    for (; c + 2 <= nctas; c += 2) { t0 += src[(size_t)c * 8 * CC]; t1 += src[(size_t)(c + 1) * 8 * CC]; }
+    for (; c < nctas; ++c) t0 += src[(size_t)c * 8 * CC];
+  }
+  gw[(size_t)m * CC + e] = t0 + t1;
+}
+
+static bool wgrad_tc4_ok(int C, int T) { return T == 4 && C >= 16 && C <= 32 && C % 4 == 0 && !(option(OPT_TC_DEBUG) & 64); }
+static int wgrad_tc4_ctas(int B, int64_t hw) {
+  const int64_t nunits = (int64_t)B * ((hw + WG_PX - 1) / WG_PX);
+  const int sms = device_info().sms;
+  return (int)(nunits < sms ? nunits : sms);
+}
+
 static bool wgrad_tc_plan(int B, int C, int T, int64_t hw, WgradTcParams& p, int& nctas, int& mchunks, int& nchunks) {
   if (C < 16 || C > 512 || C % 4 != 0 || (T != 2 && T != 4)) return false;
   if (C % 32 != 0 && C > 32) return false;                        // 16, 20, 24, 28, 32, then multiples of 32
@@ -460,13 +751,39 @@ extern "C" {
 int64_t smow_frame_mix_wgrad_tc_workspace_bytes(int B, int C, int T, int64_t hw) {
   WgradTcParams p;
   int nctas, mch, nch;
-  if (B <= 0 || hw <= 0 || !wgrad_tc_plan(B, C, T, hw, p, nctas, mch, nch)) return 0;
+  if (B <= 0 || hw <= 0) return 0;
+  if (wgrad_tc4_ok(C, T)) return (int64_t)wgrad_tc4_ctas(B, hw) * 8 * C * C * (int64_t)sizeof(float);
+  if (!wgrad_tc_plan(B, C, T, hw, p, nctas, mch, nch)) return 0;
   return (int64_t)nctas * (1 + T) * C * C * (int64_t)sizeof(float);
 }
 
 int smow_frame_mix_wgrad_tc(const float* x, const float* gy, float* gw, int B, int C, int T, int64_t hw, int shift,
                             int own_off, void* ws, int64_t ws_bytes, void* stream) {
   if (!x || !gy || !gw || B <= 0 || hw <= 0) return fail(SMOW_EINVAL, "frame_mix_wgrad_tc: bad shape / null pointer");
+  if (wgrad_tc4_ok(C, T)) {
+    if (!aligned16(x) || !aligned16(gy) || !aligned16(gw) || !ws || !aligned16(ws) ||
+        ws_bytes < smow_frame_mix_wgrad_tc_workspace_bytes(B, C, T, hw))
+      return fail(SMOW_EINVAL, "frame_mix_wgrad_tc: workspace of smow_frame_mix_wgrad_tc_workspace_bytes() bytes required");
+    Wgrad4Params q;
+    q.C = C; q.shift = ((shift % 4) + 4) % 4; q.own_off = ((own_off % 4) + 4) % 4;
+    q.ntiles = (int)((hw + WG_PX - 1) / WG_PX); q.nunits = B * q.ntiles; q.Ncw = C <= 16 ? 16 : 32;
+    q.part = reinterpret_cast<float*>(ws);
+    CUtensorMap tm_x, tm_g;
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)hw, (uint64_t)B * 4};
+    const uint64_t str[2] = {(uint64_t)C * 4, (uint64_t)hw * C * 4};
+    const uint32_t box[3] = {32, WG_PX, 1};
+    if (int rc = make_tensor_map(&tm_x, x, 3, dims, str, box, SWIZZLE_128B_ATOM32)) return rc;
+    if (int rc = make_tensor_map(&tm_g, gy, 3, dims, str, box, SWIZZLE_128B_ATOM32)) return rc;
+    const size_t smem4 = (size_t)WG4_STAGES * WG4_STAGE_BYTES + 1024;
+    if (cudaFuncSetAttribute(mix_wgrad_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4) != cudaSuccess)
+      return check_launch("frame_mix_wgrad_tc (shared-memory opt-in)");
+    const int nctas = wgrad_tc4_ctas(B, hw);
+    cudaStream_t st4 = (cudaStream_t)stream;
+    mix_wgrad_tc4_kernel<<<nctas, 128, smem4, st4>>>(tm_x, tm_g, q);
+    mix_wgrad_tc4_combine_kernel<<<dim3((C * C + 255) / 256, 5), 256, 0, st4>>>(q.part, gw, C * C, nctas);
+    count_launch(2);
+    return check_launch("frame_mix_wgrad_tc");
+  }
   WgradTcParams p;
   int nctas, mch, nch;
   if (!wgrad_tc_plan(B, C, T, hw, p, nctas, mch, nch)) return fail(SMOW_EDTYPE, "frame_mix_wgrad_tc: unsupported C = %d / T = %d", C, T);
