@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SMOW_ABI_VERSION 5
+#define SMOW_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define SMOW_API __attribute__((visibility("default")))
@@ -207,6 +207,25 @@ SMOW_API int smow_frame_mix_apply_tc(const float* in, const float* wpack, const 
 SMOW_API int64_t smow_frame_mix_wgrad_tc_workspace_bytes(int B, int C, int T, int64_t hw);
 SMOW_API int smow_frame_mix_wgrad_tc(const float* x, const float* gy, float* gw, int B, int C, int T, int64_t hw,
                          int shift, int own_off, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- N1: the OFW flow head -----------------------------------------------------------------------------------------
+ * Replaces models/SMOW_Net.py:606-608 (= models/SMOW_Net_LW.py:448-450):
+ *     seg_up = F.interpolate(seg_down, size=(2,H,W), 'trilinear', align_corners=True)
+ *     flow   = flow_make(torch.cat([x, seg_up], 1))            Conv3d(2C -> 2, 3x3x3, padding 1, no bias)
+ * with neither the up-sampled tensor nor the concat:  flow = stencil_x(x; W[:, :C]) + sum_tap bilerp(Z[tap], p + tap), where
+ *     Z[b, tap, i, j, 2t+o] = sum_{t', c} W[o, C+c, t'-t+1, kh, kw] * seg_down[b, c, t', i, j]      (tap = 3 kh + kw)
+ * is the channel contraction done at LOW resolution by the caller (a tiny einsum; up-sampling and contraction commute).
+ *   x (B,C,2,H,W) fp32 NDHWC; weight (2,2C,3,3,3) = flow_make.weight; z (B,9,h,w,4); flow (B,2,2,H,W) contiguous out.
+ * Backward: gx (B,C,2,H,W) NDHWC, gweight (2,2C,3,3,3) — ONLY the x half [:, :C] is written, gz (B,9,h,w,4); the caller
+ *   back-propagates gz through its einsum to seg_down and W[:, C:].  Deterministic (no atomics).
+ * workspace: smow_flow_head_workspace_bytes(B,C,H,W) bytes, uninitialised.  C in {16, 32, 64}, W % 4 == 0.          */
+SMOW_API int     smow_flow_head_supported(int C, int H, int W, int h, int w);
+SMOW_API int64_t smow_flow_head_workspace_bytes(int B, int C, int H, int W);
+SMOW_API int     smow_flow_head_fwd(const float* x, const float* weight, const float* z, float* flow,
+                         int B, int C, int H, int W, int h, int w, void* workspace, int64_t workspace_bytes, void* stream);
+SMOW_API int     smow_flow_head_bwd(const float* gflow, const float* x, const float* weight, float* gx, float* gweight,
+                         float* gz, int B, int C, int H, int W, int h, int w,
+                         void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -97,11 +97,49 @@ def gen_ops(ref_s):
     print("wrote", path, "%.1f KiB" % (os.path.getsize(path) / 1024))
 
 
+def gen_flow_head(ref_s):
+    """Row N1: the flow head as the REFERENCE computes it — OFW.forward (models/SMOW_Net.py:604-610) run unmodified with
+    its flow_warp replaced by a recorder, so the golden `flow` is the tensor the reference's own three lines
+    (down, F.interpolate(..., (2,128,128)), flow_make(cat)) produced.  The oracle restatement must equal it bit for
+    bit; its autograd gradients (x, coarse, weight as independent leaves) are stored beside it."""
+    from oracle import torch_ref
+    out = {}
+    g = torch.Generator().manual_seed(606)
+    for name, B, C in (("c2", 1, 2),):
+        torch.manual_seed(608 + C)
+        ofw = ref_s.OFW(C).train()
+        with torch.no_grad():
+            for p in ofw.parameters():
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+        x = torch.randn(B, C, 2, 128, 128, generator=g)         # the reference hard-codes the (2,128,128) target
+        seen = {}
+        ofw.flow_warp = lambda input, flow, size: seen.setdefault("flow", flow)      # recorder instead of the warp
+        ofw(x)
+        ref_flow = seen["flow"].detach()
+        coarse = ofw.down(x).detach()                           # train-mode BN: same batch statistics as inside forward
+        weight = ofw.flow_make.weight.detach()
+        xr, cr, wr = (t.clone().requires_grad_(True) for t in (x, coarse, weight))
+        mine = torch_ref.ref_flow_head(xr, cr, wr)
+        assert torch.equal(mine.detach(), ref_flow), name       # restatement == reference, bit for bit
+        gflow = torch.randn(mine.shape, generator=g)
+        mine.backward(gflow)
+        for k, v in (("x", x), ("coarse", coarse), ("weight", weight), ("gflow", gflow), ("flow", ref_flow),
+                     ("gx", xr.grad), ("gcoarse", cr.grad), ("gweight", wr.grad)):
+            out["flow_head/%s/%s" % (name, k)] = v.numpy().astype(np.float32)
+        print("flow_head %-6s restatement == reference OFW.forward (|flow| max %.3f)" % (name, float(ref_flow.abs().max())))
+    path = os.path.join(GOLDEN, "flow_head.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KiB" % (os.path.getsize(path) / 1024))
+
+
 def main():
     torch.manual_seed(2022)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref_s = import_reference()
+    if "--flow-head-only" in sys.argv:
+        return gen_flow_head(ref_s)
     gen_ops(ref_s)
+    gen_flow_head(ref_s)
     if "--ops-only" not in sys.argv:
         from oracle import model_fixture
         model_fixture.generate(REF, GOLDEN)

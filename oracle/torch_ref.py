@@ -92,3 +92,13 @@ def ref_cyclic_frame_mix(frames, w_shared, w_own, bias=None, shift=1, own_off=1)
             y = y + bias[f].view(1, -1, 1, 1)
         out.append(y)
     return torch.stack(out, 2)
+
+
+def ref_flow_head(x, coarse, weight):
+    """The OFW flow head — reference models/SMOW_Net.py:606-608 (= models/SMOW_Net_LW.py:448-450), with the hard-coded
+    (2,128,128) target spelled as the size of x (the same thing at 256x256 network inputs):
+        seg_down = F.interpolate(seg_down, size=(2,H,W), mode='trilinear', align_corners=True)
+        flow = self.flow_make(torch.cat([x, seg_down], dim=1))          # Conv3d(2C, 2, 3, padding=1, bias=False)
+    x (B,C,2,H,W); coarse (B,C,2,h,w) = down(x); weight (2,2C,3,3,3) -> flow (B,2,2,H,W)."""
+    up = F.interpolate(coarse, size=tuple(x.shape[2:]), mode="trilinear", align_corners=True)
+    return F.conv3d(torch.cat([x, up], dim=1), weight, None, 1, 1)

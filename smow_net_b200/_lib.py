@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmow_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 F32, BF16 = 0, 1
 NCDHW, NDHWC = 0, 1
 
@@ -42,6 +42,10 @@ SIGNATURES = {
     "smow_frame_mix_apply_tc": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i64, _i64, _i, _i, _vp]),
     "smow_frame_mix_wgrad_tc_workspace_bytes": (_i64, [_i, _i, _i, _i64]),
     "smow_frame_mix_wgrad_tc": (_i, [_fp, _fp, _fp, _i, _i, _i, _i64, _i, _i, _vp, _i64, _vp]),
+    "smow_flow_head_supported": (_i, [_i, _i, _i, _i, _i]),
+    "smow_flow_head_workspace_bytes": (_i64, [_i, _i, _i, _i]),
+    "smow_flow_head_fwd": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "smow_flow_head_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -640,3 +640,82 @@ def frame_mix_tc(x, pack, bias=None, T=4, shift=1, own_off=1, nk=True):
     if bias is not None and (tuple(bias.shape) != (T, C) or bias.dtype != torch.float32):
         raise RuntimeError("frame_mix_tc: bias must be fp32 (T,C)")
     return _FrameMixTC.apply(x, pack, bias, T, shift, own_off, nk)
+
+
+# ----------------------------------------------------------------------------- N1: the OFW flow head
+def flow_head_fwd_bytes(B, C, H, W, h, w):
+    """Algorithmic bytes: x read once, the low-resolution table read once, the flow written."""
+    return B * (2 * C * H * W * 4 + 9 * h * w * 16 + 16 * H * W)
+
+
+def flow_head_bwd_bytes(B, C, H, W, h, w):
+    """d x written once, x read once (for d W), the flow gradient read, d Z written."""
+    return B * (4 * C * H * W * 4 + 16 * H * W + 9 * h * w * 16)
+
+
+def flow_head_supported(x, coarse):
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.shape[2] == 2 and x.shape[0] > 0 and coarse.dim() == 5
+            and bool(_lib.load().smow_flow_head_supported(int(x.shape[1]), int(x.shape[3]), int(x.shape[4]),
+                                                          int(coarse.shape[3]), int(coarse.shape[4]))))
+
+
+class _FlowHead(torch.autograd.Function):
+    """flow = stencil(x; W[:, :C]) + sum_tap bilerp(z[tap], p + tap) — see include/smow_b200.h (row N1)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, z):
+        B, C, _, H, W = x.shape
+        h, w = z.shape[2], z.shape[3]
+        x = x.contiguous(memory_format=torch.channels_last_3d)
+        weight, z = weight.contiguous(), z.contiguous()
+        flow = torch.empty((B, 2, 2, H, W), dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        n = int(lib.smow_flow_head_workspace_bytes(B, C, H, W))
+        ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device_of(x):
+            _meta(B=B, C=C, H=H, W=W, h=h, w=w)
+            _call("flow_head_fwd", flow_head_fwd_bytes(B, C, H, W, h, w), lib.smow_flow_head_fwd,
+                  x.data_ptr(), weight.data_ptr(), z.data_ptr(), flow.data_ptr(), B, C, H, W, h, w, ws.data_ptr(), n, _stream())
+        ctx.save_for_backward(x, weight)
+        ctx.zshape = tuple(z.shape)
+        return flow
+
+    @staticmethod
+    def backward(ctx, gflow):
+        x, weight = ctx.saved_tensors
+        B, C, _, H, W = x.shape
+        h, w = ctx.zshape[2], ctx.zshape[3]
+        gflow = gflow.contiguous().float()
+        gx = torch.empty_like(x, memory_format=torch.channels_last_3d)
+        gweight = torch.zeros_like(weight)                         # the kernel fills the x half; the seg half comes through z
+        gz = torch.empty(ctx.zshape, dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        n = int(lib.smow_flow_head_workspace_bytes(B, C, H, W))
+        ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device_of(x):
+            _meta(B=B, C=C, H=H, W=W, h=h, w=w)
+            _call("flow_head_bwd", flow_head_bwd_bytes(B, C, H, W, h, w), lib.smow_flow_head_bwd,
+                  gflow.data_ptr(), x.data_ptr(), weight.data_ptr(), gx.data_ptr(), gweight.data_ptr(), gz.data_ptr(),
+                  B, C, H, W, h, w, ws.data_ptr(), n, _stream())
+        return gx, gweight, gz
+
+
+def flow_head(x, coarse, weight):
+    """The OFW flow head in one pass (reference models/SMOW_Net.py:606-608):
+    ``flow_make(cat([x, interpolate(coarse, (2,H,W), trilinear, align_corners=True)], 1))`` with neither the up-sampled
+    tensor nor the concat.  x (B,C,2,H,W), coarse (B,C,2,h,w) = ``down(x)``, weight (2,2C,3,3,3) -> flow (B,2,2,H,W)."""
+    _require_cuda(x, coarse, weight)
+    if not flow_head_supported(x, coarse):
+        raise RuntimeError("flow_head: needs an fp32 CUDA (B,C,2,H,W) stack with C in {16,32,64}, W %% 4 == 0, got %s / coarse %s"
+                           % (tuple(x.shape), tuple(coarse.shape)))
+    B, C = x.shape[0], x.shape[1]
+    if tuple(weight.shape) != (2, 2 * C, 3, 3, 3) or tuple(coarse.shape[:3]) != (B, C, 2) or weight.dtype != torch.float32 \
+            or coarse.dtype != torch.float32:
+        raise RuntimeError("flow_head: weight must be fp32 (2,2C,3,3,3) and coarse fp32 (B,C,2,h,w)")
+    # channel contraction of the seg half at LOW resolution (up-sampling and contraction commute): output frame t sees input
+    # frame t' through the temporal tap kt = t' - t + 1 (the third tap always falls on the zero padding)
+    wc = weight[:, C:]
+    wsel = torch.stack((wc[:, :, 1:3], wc[:, :, 0:2]), 0)                         # (t, o, c, t', kh, kw)
+    z = torch.einsum("tocskl,bcsij->bklijto", wsel, coarse)                        # (B, 3, 3, h, w, 2, 2)
+    z = z.reshape(B, 9, coarse.shape[3], coarse.shape[4], 4)
+    return _FlowHead.apply(x, weight, z)

@@ -67,6 +67,7 @@ def use_oracle_ops(monkeypatch):
     # comparison never has the CUDA kernels of those rows in both arms
     from smow_net_b200.models import blocks
     monkeypatch.setattr(ops, "semantic_tokens", torch_ref.ref_semantic_tokens)
+    monkeypatch.setattr(ops, "flow_head", torch_ref.ref_flow_head)            # row N1
 
     def mix(frames5d, shared, own, shift=1, own_off=1):
         T, bias = len(own), None

@@ -449,3 +449,58 @@ def test_warp_ndhwc_forward_kernels_agree_bit_for_bit(case, variants):
         b = ops.flow_warp(x, flow, (H, W))
     assert torch.equal(a, b)
     assert float((a - torch_ref.ref_flow_warp(x, flow)).abs().max()) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ row N1: flow head
+@pytest.fixture
+def strict_conv():
+    """The oracle's F.conv3d must run in full fp32 (cuDNN's TF32 default would make the CHECKER the imprecise side)."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("case", [(2, 16, 128, 128, 16, 16), (1, 32, 128, 128, 16, 16), (2, 16, 24, 40, 3, 5),
+                                  (1, 64, 16, 16, 2, 2), (3, 16, 9, 12, 1, 1), (1, 32, 40, 36, 5, 5)])
+def test_flow_head_matches_the_oracle(case, strict_conv):
+    """Row N1: ops.flow_head (up-sample + concat + flow_make in one pass, nothing materialised) against the oracle's
+    restatement of reference models/SMOW_Net.py:606-608 (interpolate + cat + conv3d) on the same device, strict fp32:
+    the flow, d x, d coarse and d weight.  Tolerance 1e-5 of each tensor's scale (the kernel contracts the seg half at low
+    resolution, i.e. it re-associates the same fp32 sums).  Ragged shapes cover image borders and coarse grids of 1."""
+    from oracle import torch_ref
+    from smow_net_b200 import _lib
+    B, C, H, W, h, w = case
+    g = torch.Generator().manual_seed(B * 100 + C + H)
+    x = torch.randn(B, C, 2, H, W, generator=g).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    coarse = torch.randn(B, C, 2, h, w, generator=g).to(DEV)
+    weight = (torch.randn(2, 2 * C, 3, 3, 3, generator=g) / (2 * C * 18) ** 0.5).to(DEV)
+    gflow = torch.randn(B, 2, 2, H, W, generator=g).to(DEV)
+    res = []
+    for fn in (ops.flow_head, torch_ref.ref_flow_head):
+        xi, ci, wi = (t.detach().clone(memory_format=torch.preserve_format).requires_grad_(True) for t in (x, coarse, weight))
+        before = _lib.launch_count()
+        flow = fn(xi, ci, wi)
+        flow.backward(gflow)
+        res.append((flow.detach(), xi.grad, ci.grad, wi.grad, _lib.launch_count() - before))
+    assert res[0][4] == 7 and res[1][4] == 0                       # pack + fwd, pack + d x + d Z + d W + reduce
+    assert res[0][0].is_contiguous() and res[0][0].shape == (B, 2, 2, H, W)
+    for a, b, name in zip(res[0][:4], res[1][:4], ("flow", "gx", "gcoarse", "gweight")):
+        assert a.shape == b.shape
+        err = float((a - b).abs().max()) / max(1.0, float(b.abs().max()))
+        assert err <= 1e-5, (name, err)
+
+
+def test_flow_head_is_deterministic_and_refuses_cpu():
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 16, 2, 32, 32, generator=g).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    coarse, weight = torch.randn(2, 16, 2, 4, 4, generator=g).to(DEV), torch.randn(2, 32, 3, 3, 3, generator=g).to(DEV)
+    outs = []
+    for _ in range(2):
+        xi, ci, wi = (t.detach().clone(memory_format=torch.preserve_format).requires_grad_(True) for t in (x, coarse, weight))
+        f = ops.flow_head(xi, ci, wi)
+        f.sum().backward()
+        outs.append((f.detach(), xi.grad, ci.grad, wi.grad))
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
+    with pytest.raises(RuntimeError):
+        ops.flow_head(x.cpu(), coarse.cpu(), weight.cpu())

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import torch
 
+import helpers
 from helpers import golden_cases
 from oracle import c_oracle, torch_ref
 
@@ -93,3 +94,22 @@ def test_c_oracle_tokenizer_and_frame_mix_match_the_torch_restatements():
         got = c_oracle.frame_mix_fwd(x.numpy(), ws.numpy(), wo.numpy(), None if bb is None else bb.numpy())
         want = torch_ref.ref_cyclic_frame_mix(x.double(), ws.double(), wo.double(), None if bb is None else bb.double()).numpy()
         assert np.abs(got - want).max() <= 1e-5
+
+
+def test_flow_head_restatement_reproduces_the_reference_golden():
+    """Row N1: oracle/torch_ref.py::ref_flow_head (interpolate + cat + conv3d, reference models/SMOW_Net.py:606-608) against
+    tests/golden/flow_head.npz, whose `flow` was recorded from the REAL reference's OFW.forward (oracle/make_golden.py
+    ::gen_flow_head) — forward bit for bit, autograd gradients to fp32 rounding."""
+    import torch
+    from oracle import torch_ref
+    z = helpers.load_golden("flow_head.npz")
+    names = sorted({k.split("/")[1] for k in z.files})
+    assert names
+    for n in names:
+        t = {k: torch.from_numpy(z["flow_head/%s/%s" % (n, k)]) for k in ("x", "coarse", "weight", "gflow", "flow", "gx", "gcoarse", "gweight")}
+        x, c, w = (t[k].clone().requires_grad_(True) for k in ("x", "coarse", "weight"))
+        flow = torch_ref.ref_flow_head(x, c, w)
+        assert torch.equal(flow.detach(), t["flow"]), n
+        flow.backward(t["gflow"])
+        for got, want in ((x.grad, t["gx"]), (c.grad, t["gcoarse"]), (w.grad, t["gweight"])):
+            assert float((got - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max())), n
