@@ -15,8 +15,24 @@
 // fp32, x NDHWC (channels_last_3d), flow contiguous (B,2,2,H,W) = [b][o][t][y][x].  Bandwidth / FP32-issue bound, N = 2
 // output channels: nothing here for tensor cores.
 #include "common.cuh"
+#include "bulk.cuh"
 
 namespace smow {
+
+// 4-byte asynchronous copy global -> shared with zero fill when !valid (all copies of a tile are in flight at once)
+__device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gmem_src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(valid ? 4 : 0) : "memory");
+}
+// gradient tile with a one-row / four-column zero halo: gs[q][r][4 + x] = g[b][o][t][y0 - 1 + r][x]   (q = 2t + o)
+__device__ __forceinline__ void load_grad_tile(float* gs, const float* __restrict__ g, int b, int y0, int R2, int LD, int H, int W) {
+  const int n = 4 * R2 * LD;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int col = i % LD - 4, rr = i / LD, r = rr % R2, q = rr / R2;
+    const int yy = y0 + r - 1, t = q >> 1, o = q & 1;
+    const bool ok = col >= 0 && col < W && yy >= 0 && yy < H;
+    cp_async4_zfill(gs + i, ok ? g + ((((size_t)b * 2 + o) * 2 + t) * H + yy) * W + col : g, ok);
+  }
+}
 
 // ATen's align_corners=True source index (UpSample.h area_pixel_compute_source_index): src = dst * (in-1)/(out-1)
 struct UpIdx { int i0, i1; float l0, l1; };
@@ -54,9 +70,11 @@ flow_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wxp,
   float* ws = sm;                                   // [2][9][4][C]
   float* zs = ws + 72 * C;                          // [9][h*w][4]
   const int b = blockIdx.y, y0 = blockIdx.x * rows_per_cta;
-  for (int i = threadIdx.x; i < 72 * C / 4; i += 256) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wxp) + i);
+  for (int i = threadIdx.x; i < 72 * C / 4; i += 256) cp_async16(reinterpret_cast<float4*>(ws) + i, reinterpret_cast<const float4*>(wxp) + i);
   const float4* zb = reinterpret_cast<const float4*>(z) + (size_t)b * 9 * h * w;
-  for (int i = threadIdx.x; i < 9 * h * w; i += 256) reinterpret_cast<float4*>(zs)[i] = __ldg(zb + i);
+  for (int i = threadIdx.x; i < 9 * h * w; i += 256) cp_async16(reinterpret_cast<float4*>(zs) + i, zb + i);
+  cp_async_commit();
+  cp_async_wait_all();
   __syncthreads();
   const int quads = W >> 2;
   const float sy = up_scale(h, H), sx = up_scale(w, W);
@@ -68,34 +86,39 @@ flow_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wxp,
     for (int p = 0; p < 4; ++p)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[p][q] = 0.f;
-    // ---- x half: rows y-1..y+1, columns xq-1..xq+4 of both frames
-    for (int tp = 0; tp < 2; ++tp) {
-      for (int kh = 0; kh < 3; ++kh) {
-        const int yy = y + kh - 1;
-        if (yy < 0 || yy >= H) continue;
-        const float* row = x + (((size_t)(b * 2 + tp) * H + yy) * W) * C;
-        for (int cv = 0; cv < C / 4; ++cv) {
-          float4 xv[6];
+    // ---- x half: rows y-1..y+1, columns xq-1..xq+4 of both frames; iterations (t', kh, channel vector) are flattened and the
+    // six taps of the NEXT iteration are loaded while the current ones are consumed
+    constexpr int Q4 = C / 4, NIT = 6 * Q4;
+    auto load6 = [&](int it, float4 (&xv)[6]) {
+      const int cv = it % Q4, kh = (it / Q4) % 3, tp = it / (3 * Q4), yy = y + kh - 1;
+      const bool rowok = yy >= 0 && yy < H;
+      const float* row = x + (((size_t)(b * 2 + tp) * H + (rowok ? yy : 0)) * W) * C;
 #pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const int xx = xq + j - 1;
-            xv[j] = (xx >= 0 && xx < W) ? __ldg(reinterpret_cast<const float4*>(row + (size_t)xx * C) + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+      for (int j = 0; j < 6; ++j) {
+        const int xx = xq + j - 1;
+        xv[j] = (rowok && xx >= 0 && xx < W) ? __ldg(reinterpret_cast<const float4*>(row + (size_t)xx * C) + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 cur[6], nxt[6];
+    load6(0, cur);
+    for (int it = 0; it < NIT; ++it) {
+      if (it + 1 < NIT) load6(it + 1, nxt);
+      const int cv = it % Q4, kh = (it / Q4) % 3, tp = it / (3 * Q4);
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const float4* wv = reinterpret_cast<const float4*>(ws + ((tp * 9 + kh * 3 + kw) * 4) * C) + cv;
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4* wv = reinterpret_cast<const float4*>(ws + ((tp * 9 + kh * 3 + kw) * 4) * C) + cv;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 wq = wv[q * (C / 4)];
+        for (int q = 0; q < 4; ++q) {
+          const float4 wq = wv[q * Q4];
 #pragma unroll
-              for (int p = 0; p < 4; ++p) {
-                const float4 v = xv[p + kw];
-                acc[p][q] = fmaf(v.x, wq.x, fmaf(v.y, wq.y, fmaf(v.z, wq.z, fmaf(v.w, wq.w, acc[p][q]))));
-              }
-            }
+          for (int p = 0; p < 4; ++p) {
+            const float4 v = cur[p + kw];
+            acc[p][q] = fmaf(v.x, wq.x, fmaf(v.y, wq.y, fmaf(v.z, wq.z, fmaf(v.w, wq.w, acc[p][q]))));
           }
         }
       }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) cur[j] = nxt[j];
     }
     // ---- seg half: 9 bilinear look-ups into the low-resolution table
     for (int kh = 0; kh < 3; ++kh) {
@@ -140,12 +163,10 @@ flow_head_bwd_x_kernel(const float* __restrict__ g, const float* __restrict__ wx
   float* ws = sm;                                   // [2][9][4][C]
   float* gs = ws + 72 * C;                          // [4 (t*2+o)][rows_per_cta + 2][W + 8]   (column x stored at x + 4)
   const int b = blockIdx.y, y0 = blockIdx.x * rows_per_cta, LD = W + 8, R2 = rows_per_cta + 2;
-  for (int i = threadIdx.x; i < 72 * C / 4; i += 256) reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(wxp) + i);
-  for (int i = threadIdx.x; i < 4 * R2 * LD; i += 256) {
-    const int col = i % LD - 4, r = (i / LD) % R2, q = i / (LD * R2);
-    const int yy = y0 + r - 1, t = q >> 1, o = q & 1;
-    gs[i] = (col >= 0 && col < W && yy >= 0 && yy < H) ? __ldg(g + ((((size_t)b * 2 + o) * 2 + t) * H + yy) * W + col) : 0.f;
-  }
+  for (int i = threadIdx.x; i < 72 * C / 4; i += 256) cp_async16(reinterpret_cast<float4*>(ws) + i, reinterpret_cast<const float4*>(wxp) + i);
+  load_grad_tile(gs, g, b, y0, R2, LD, H, W);
+  cp_async_commit();
+  cp_async_wait_all();
   __syncthreads();
   constexpr int Q = C / 4;
   const int quads = W >> 2;
@@ -192,20 +213,28 @@ flow_head_bwd_x_kernel(const float* __restrict__ g, const float* __restrict__ wx
 
 // ---- backward: d Z (transposed bilinear of the nine shifted gradient planes) ------------------------------------------
 // gz[b,tap,i,j,q] = sum_{P,Q} Ry[P][i] Rx[Q][j] [P-kh+1, Q-kw+1 inside] g[b,q][P-kh+1][Q-kw+1]     (P,Q = sampling position)
-// one CTA per (b, q): U_kh[i][Q'] = sum_P Ry[P][i] g[P-kh+1][Q'] (Q' = source column), then the column pass per kw.
+// one CTA per (b, q, kh): U[i][Q'] = sum_P Ry[P][i] g[P-kh+1][Q'] (Q' = source column), then the column pass for kw = 0..2.
+// The bilinear source index / weights of every sampling row and column are tabulated once in shared memory.
 __global__ void __launch_bounds__(256)
 flow_head_bwd_z_kernel(const float* __restrict__ g, float* __restrict__ gz, int H, int W, int h, int w) {
   extern __shared__ __align__(16) float sm[];
   float* gp = sm;                                   // [H][W] gradient plane
-  float* U = gp + H * W;                            // [3][h][W]
-  const int b = blockIdx.x >> 2, q = blockIdx.x & 3, t = q >> 1, o = q & 1;
+  float* U = gp + H * W;                            // [h][W]
+  float* l1y = U + h * W;                           // [H] weight of the second source row
+  float* l1x = l1y + H;                             // [W]
+  int* i0y = reinterpret_cast<int*>(l1x + W);       // [H] first source row | second << 16
+  int* i0x = i0y + H;                               // [W]
+  const int kh = blockIdx.x % 3, q = (blockIdx.x / 3) & 3, b = blockIdx.x / 12, t = q >> 1, o = q & 1;
   const float* src = g + (((size_t)b * 2 + o) * 2 + t) * H * W;
-  for (int i = threadIdx.x; i < H * W / 4; i += 256) reinterpret_cast<float4*>(gp)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-  __syncthreads();
+  for (int i = threadIdx.x; i < H * W / 4; i += 256) cp_async16(reinterpret_cast<float4*>(gp) + i, reinterpret_cast<const float4*>(src) + i);
+  cp_async_commit();
   const float sy = up_scale(h, H), sx = up_scale(w, W);
-  // row pass: U[kh][i][c] = sum over sampling rows P with P-kh+1 in [0,H): Ry[P][i] * g[P-kh+1][c]
-  for (int e = threadIdx.x; e < 3 * h * W; e += 256) {
-    const int c = e % W, i = (e / W) % h, kh = e / (W * h);
+  for (int P = threadIdx.x; P < H; P += 256) { const UpIdx u = up_index(P, h, sy); l1y[P] = u.l1; i0y[P] = u.i0 | (u.i1 << 16); }
+  for (int Q = threadIdx.x; Q < W; Q += 256) { const UpIdx u = up_index(Q, w, sx); l1x[Q] = u.l1; i0x[Q] = u.i0 | (u.i1 << 16); }
+  cp_async_wait_all();
+  __syncthreads();
+  for (int e = threadIdx.x; e < h * W; e += 256) {
+    const int c = e % W, i = e / W;
     // rows P whose bilinear footprint contains node i lie in [ (i-1)/sy , (i+1)/sy ]
     int lo = sy > 0.f ? (int)floorf((float)(i - 1) / sy) - 1 : 0, hi = sy > 0.f ? (int)ceilf((float)(i + 1) / sy) + 1 : H - 1;
     if (lo < 0) lo = 0;
@@ -214,17 +243,18 @@ flow_head_bwd_z_kernel(const float* __restrict__ g, float* __restrict__ gz, int 
     for (int P = lo; P <= hi; ++P) {
       const int ys = P - kh + 1;
       if (ys < 0 || ys >= H) continue;
-      const UpIdx u = up_index(P, h, sy);
+      const int pk = i0y[P];
+      const float l1 = l1y[P];
       float wgt = 0.f;
-      if (u.i0 == i) wgt += u.l0;
-      if (u.i1 == i) wgt += u.l1;
+      if ((pk & 0xffff) == i) wgt += 1.f - l1;
+      if ((pk >> 16) == i) wgt += l1;
       if (wgt != 0.f) acc = fmaf(wgt, gp[ys * W + c], acc);
     }
     U[e] = acc;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 9 * h * w; e += 256) {
-    const int j = e % w, i = (e / w) % h, tap = e / (w * h), kh = tap / 3, kw = tap - kh * 3;
+  for (int e = threadIdx.x; e < 3 * h * w; e += 256) {
+    const int j = e % w, i = (e / w) % h, kw = e / (w * h);
     int lo = sx > 0.f ? (int)floorf((float)(j - 1) / sx) - 1 : 0, hi = sx > 0.f ? (int)ceilf((float)(j + 1) / sx) + 1 : W - 1;
     if (lo < 0) lo = 0;
     if (hi > W - 1) hi = W - 1;
@@ -232,24 +262,27 @@ flow_head_bwd_z_kernel(const float* __restrict__ g, float* __restrict__ gz, int 
     for (int Q = lo; Q <= hi; ++Q) {
       const int xs = Q - kw + 1;
       if (xs < 0 || xs >= W) continue;
-      const UpIdx u = up_index(Q, w, sx);
+      const int pk = i0x[Q];
+      const float l1 = l1x[Q];
       float wgt = 0.f;
-      if (u.i0 == j) wgt += u.l0;
-      if (u.i1 == j) wgt += u.l1;
-      if (wgt != 0.f) acc = fmaf(wgt, U[(kh * h + i) * W + xs], acc);
+      if ((pk & 0xffff) == j) wgt += 1.f - l1;
+      if ((pk >> 16) == j) wgt += l1;
+      if (wgt != 0.f) acc = fmaf(wgt, U[i * W + xs], acc);
     }
-    gz[(((size_t)b * 9 + tap) * h * w + (size_t)i * w + j) * 4 + q] = acc;
+    gz[(((size_t)b * 9 + kh * 3 + kw) * h * w + (size_t)i * w + j) * 4 + q] = acc;
   }
 }
 
 // ---- backward: d W_x ---------------------------------------------------------------------------------------------------
-// gw[o,c,t'-t+1,kh,kw] = sum_{b,y',x'} g[b,o,t,y'-kh+1,x'-kw+1] * x[b,c,t',y',x'].  CTA = (row band of one (pair, t')); thread =
-// (channel c, group); a group owns combos {grp, grp+G, ...} of the 36 (tap, t, o).  part[cta][36][C].
+// gw[o,c,t'-t+1,kh,kw] = sum_{b,y',x'} g[b,o,t,y'-kh+1,x'-kw+1] * x[b,c,t',y',x']: a [36 combos x pixels] . [pixels x C] product per
+// (pair, t', row band).  thread = (6 combos, 4 channels) register tile over every NS-th column of the band; the NS column
+// slices are added in a fixed order through shared memory.  part[cta][36][C].
 template <int C>
 __global__ void __launch_bounds__(256)
 flow_head_bwd_w_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ part, int H, int W,
                        int rows_per_cta) {
   extern __shared__ __align__(16) float sm[];
+  constexpr int Q = C / 4, TILES = 6 * Q, NS = 256 / TILES;           // C = 16: 24 tiles x 10 slices; 32: 48 x 5; 64: 96 x 2
   const int LD = W + 8, R2 = rows_per_cta + 2;
   float* gs = sm;                                   // [4][R2][LD]
   float* xs = gs + 4 * R2 * LD;                     // [rows][W][C]
@@ -257,68 +290,76 @@ flow_head_bwd_w_kernel(const float* __restrict__ g, const float* __restrict__ x,
   const int band = blockIdx.x % bands, tp = (blockIdx.x / bands) & 1, b = blockIdx.x / (2 * bands);
   const int y0 = band * rows_per_cta;
   const int nrows = H - y0 < rows_per_cta ? H - y0 : rows_per_cta;
-  for (int i = threadIdx.x; i < 4 * R2 * LD; i += 256) {
-    const int col = i % LD - 4, r = (i / LD) % R2, q = i / (LD * R2);
-    const int yy = y0 + r - 1, t = q >> 1, o = q & 1;
-    gs[i] = (col >= 0 && col < W && yy >= 0 && yy < H) ? __ldg(g + ((((size_t)b * 2 + o) * 2 + t) * H + yy) * W + col) : 0.f;
-  }
+  load_grad_tile(gs, g, b, y0, R2, LD, H, W);
   const float4* xsrc = reinterpret_cast<const float4*>(x + (((size_t)(b * 2 + tp) * H + y0) * W) * C);
-  for (int i = threadIdx.x; i < nrows * W * C / 4; i += 256) reinterpret_cast<float4*>(xs)[i] = __ldg(xsrc + i);
+  for (int i = threadIdx.x; i < nrows * W * C / 4; i += 256) cp_async16(reinterpret_cast<float4*>(xs) + i, xsrc + i);
+  cp_async_commit();
+  cp_async_wait_all();
   __syncthreads();
-  constexpr int G = 256 / C, NA = (36 + G - 1) / G;
-  const int c = threadIdx.x % C, grp = threadIdx.x / C;
-  float acc[NA];
-  int off[NA];                                       // offset of the combo's gradient sample relative to (row r+1, col x'+4)
+  const int tile = threadIdx.x % TILES, slice = threadIdx.x / TILES;
+  const int cv = tile % Q, cg = tile / Q;                             // combos 6*cg .. 6*cg+5
+  float4 acc[6];
+  int off[6];                                        // gradient sample of combo a relative to (row r, column xx)
 #pragma unroll
-  for (int a = 0; a < NA; ++a) {
-    acc[a] = 0.f;
-    const int combo = grp + a * G;                  // combo = tap*4 + q
-    if (combo < 36) {
-      const int tap = combo >> 2, q = combo & 3, kh = tap / 3, kw = tap - kh * 3;
-      off[a] = (q * R2 + (1 - kh + 1)) * LD + 4 - kw + 1;
-    } else {
-      off[a] = -1;
+  for (int a = 0; a < 6; ++a) {
+    acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int combo = 6 * cg + a, tap = combo >> 2, q = combo & 3, kh = tap / 3, kw = tap - kh * 3;
+    off[a] = (q * R2 + (2 - kh)) * LD + 5 - kw;
+  }
+  if (slice < NS) {
+    for (int r = 0; r < nrows; ++r) {
+      const float* xrow = xs + (size_t)r * W * C + 4 * cv;
+      const float* grow = gs + r * LD;
+#pragma unroll 2
+      for (int xx = slice; xx < W; xx += NS) {
+        const float4 xv = *reinterpret_cast<const float4*>(xrow + (size_t)xx * C);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          const float gg = grow[off[a] + xx];
+          acc[a].x = fmaf(gg, xv.x, acc[a].x); acc[a].y = fmaf(gg, xv.y, acc[a].y);
+          acc[a].z = fmaf(gg, xv.z, acc[a].z); acc[a].w = fmaf(gg, xv.w, acc[a].w);
+        }
+      }
     }
   }
-  for (int r = 0; r < nrows; ++r) {
-    for (int xx = 0; xx < W; ++xx) {
-      const float xv = xs[(r * W + xx) * C + c];
-      const int basep = r * LD + xx;
+  __syncthreads();
+  float* red = sm;                                   // [NS][36][C]  (<= 10*36*16*4 = 23 KB)
+  if (slice < NS) {
 #pragma unroll
-      for (int a = 0; a < NA; ++a)
-        if (off[a] >= 0) acc[a] = fmaf(gs[off[a] + basep], xv, acc[a]);
-    }
+    for (int a = 0; a < 6; ++a) reinterpret_cast<float4*>(red + ((size_t)slice * 36 + 6 * cg + a) * C)[cv] = acc[a];
   }
-#pragma unroll
-  for (int a = 0; a < NA; ++a) {
-    const int combo = grp + a * G;
-    if (combo < 36) part[((size_t)blockIdx.x * 36 + combo) * C + c] = acc[a];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 36 * C; e += 256) {
+    float tsum = 0.f;
+    for (int k = 0; k < NS; ++k) tsum += red[(size_t)k * 36 * C + e];
+    part[(size_t)blockIdx.x * 36 * C + e] = tsum;
   }
 }
 
-// gw (2, 2C, 3,3,3): only the x half [:, :C] is written here.  One thread per (o, c, kt, tap); the temporal tap kt = t' - t + 1
-// collects (t',t) = (0,1) for kt = 0, (0,0) and (1,1) for kt = 1, (1,0) for kt = 2.  Fixed summation order.
+// gw (2, 2C, 3,3,3): only the x half [:, :C] is written here.  One WARP per (o, c, kt, tap); the temporal tap kt = t' - t + 1
+// collects (t',t) = (0,1) for kt = 0, (0,0) and (1,1) for kt = 1, (1,0) for kt = 2.  Lanes stride over the per-CTA partials,
+// then a fixed shuffle tree: deterministic.
 __global__ void __launch_bounds__(256)
 flow_head_bwd_w_reduce_kernel(const float* __restrict__ part, float* __restrict__ gw, int C, int nctas, int bands) {
-  const int e = blockIdx.x * 256 + threadIdx.x;
+  const int e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (e >= 2 * C * 27) return;
   const int tap = e % 9, kt = (e / 9) % 3, c = (e / 27) % C, o = e / (27 * C);
-  const int per_b = 2 * bands;
+  const int npairs = nctas / (2 * bands);                              // = B
   float total = 0.f;
   for (int tp = 0; tp < 2; ++tp) {
     const int t = tp - kt + 1;
     if (t < 0 || t > 1) continue;
     const int combo = tap * 4 + t * 2 + o;
-    float t0 = 0.f, t1 = 0.f;
-    for (int cta = tp * bands; cta < nctas; cta += per_b) {       // CTAs are ordered (b, t', band)
-      for (int k = 0; k < bands; k += 2) {
-        t0 += part[((size_t)(cta + k) * 36 + combo) * C + c];
-        if (k + 1 < bands) t1 += part[((size_t)(cta + k + 1) * 36 + combo) * C + c];
-      }
+    float acc = 0.f;
+    for (int k = lane; k < npairs * bands; k += 32) {                  // CTAs are ordered (b, t', band)
+      const int bb = k / bands, band = k - bb * bands;
+      acc += part[((size_t)((bb * 2 + tp) * bands + band) * 36 + combo) * C + c];
     }
-    total += t0 + t1;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    total += acc;
   }
-  gw[(((size_t)o * 2 * C + c) * 3 + kt) * 9 + tap] = total;
+  if (lane == 0) gw[(((size_t)o * 2 * C + c) * 3 + kt) * 9 + tap] = total;
 }
 
 template <typename K> static int opt_in_smem(K kernel, size_t bytes, const char* what) {
@@ -328,7 +369,7 @@ template <typename K> static int opt_in_smem(K kernel, size_t bytes, const char*
 }
 static bool flow_head_ok(int C, int H, int W, int h, int w) {
   return (C == 16 || C == 32 || C == 64) && W % 4 == 0 && W >= 4 && H >= 1 && h >= 1 && w >= 1 && (size_t)9 * h * w * 16 <= 96 * 1024 &&
-         (size_t)H * W * 4 + (size_t)3 * h * W * 4 <= 200 * 1024;
+         (size_t)H * W * 4 + (size_t)h * W * 4 + 8 * (size_t)(H + W) <= 200 * 1024 && h < 32768 && w < 32768;
 }
 static int fh_rows_w(int C, int W) {                  // rows per CTA of the d W kernel: x band + gradient halo must fit
   int rows = 8;
@@ -405,13 +446,15 @@ int smow_flow_head_bwd(const float* gflow, const float* x, const float* weight, 
     }
   }
   {   // d Z
-    const size_t smem = ((size_t)H * W + (size_t)3 * h * W) * 4;
+    const size_t smem = ((size_t)H * W + (size_t)h * W + 2 * (size_t)(H + W)) * 4;
     if ((rc = opt_in_smem(flow_head_bwd_z_kernel, smem, "flow_head_bwd_z"))) return rc;
-    flow_head_bwd_z_kernel<<<B * 4, 256, smem, st>>>(gflow, gz, H, W, h, w);
+    flow_head_bwd_z_kernel<<<B * 12, 256, smem, st>>>(gflow, gz, H, W, h, w);
   }
   {   // d W_x
     const int rows = fh_rows_w(C, W), bands = (H + rows - 1) / rows, nctas = B * 2 * bands;
-    const size_t smem = ((size_t)4 * (rows + 2) * (W + 8) + (size_t)rows * W * C) * 4;
+    size_t smem = ((size_t)4 * (rows + 2) * (W + 8) + (size_t)rows * W * C) * 4;
+    const size_t red = (size_t)(256 / (6 * (C / 4))) * 36 * C * 4;   // the slice-reduction scratch re-uses the tile space
+    if (smem < red) smem = red;
     switch (C) {
       case 16: if ((rc = opt_in_smem(flow_head_bwd_w_kernel<16>, smem, "flow_head_bwd_w"))) return rc;
                flow_head_bwd_w_kernel<16><<<nctas, 256, smem, st>>>(gflow, x, part, H, W, rows); break;
@@ -420,7 +463,7 @@ int smow_flow_head_bwd(const float* gflow, const float* x, const float* weight, 
       default: if ((rc = opt_in_smem(flow_head_bwd_w_kernel<64>, smem, "flow_head_bwd_w"))) return rc;
                flow_head_bwd_w_kernel<64><<<nctas, 256, smem, st>>>(gflow, x, part, H, W, rows); break;
     }
-    flow_head_bwd_w_reduce_kernel<<<(2 * 27 * C + 255) / 256, 256, 0, st>>>(part, gweight, C, nctas, bands);
+    flow_head_bwd_w_reduce_kernel<<<(2 * 27 * C + 7) / 8, 256, 0, st>>>(part, gweight, C, nctas, bands);
   }
   count_launch(5);
   return check_launch("flow_head_bwd");

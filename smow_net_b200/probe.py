@@ -111,6 +111,24 @@ def build(name, m, dev, gen, sigma=0.3):
             fn = lambda: _lib.check(lib.smow_frame_mix_wgrad(x.data_ptr(), y.data_ptr(), gw.data_ptr(), B, C, hw, ws.data_ptr(), n, st()), name)  # noqa: E731
         nb = ops.frame_mix_wgrad_bytes(B, C, T, hw)
         return fn, nb, nb, (x, y, gw, ws)
+    if name in ("flow_head_fwd", "flow_head_bwd"):
+        B, C, H, W, h, w = m["B"], m["C"], m["H"], m["W"], m["h"], m["w"]
+        x = _t((B, C, 2, H, W), dev, torch.float32, _lib.NDHWC, gen)
+        weight = torch.randn(2, 2 * C, 3, 3, 3, device=dev, generator=gen) / (36 * C) ** 0.5
+        z = torch.randn(B, 9, h, w, 4, device=dev, generator=gen)
+        flow = torch.randn(B, 2, 2, H, W, device=dev, generator=gen)
+        n = int(lib.smow_flow_head_workspace_bytes(B, C, H, W))
+        ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        if name == "flow_head_fwd":
+            fn = lambda: _lib.check(lib.smow_flow_head_fwd(x.data_ptr(), weight.data_ptr(), z.data_ptr(), flow.data_ptr(), B, C, H, W,  # noqa: E731
+                                                           h, w, ws.data_ptr(), n, st()), name)
+            nb = ops.flow_head_fwd_bytes(B, C, H, W, h, w)
+            return fn, nb, nb, (x, z, flow, ws)
+        gx, gw, gz = torch.empty_like(x), torch.empty_like(weight), torch.empty_like(z)
+        fn = lambda: _lib.check(lib.smow_flow_head_bwd(flow.data_ptr(), x.data_ptr(), weight.data_ptr(), gx.data_ptr(), gw.data_ptr(),  # noqa: E731
+                                                       gz.data_ptr(), B, C, H, W, h, w, ws.data_ptr(), n, st()), name)
+        nb = ops.flow_head_bwd_bytes(B, C, H, W, h, w)
+        return fn, nb, nb, (x, z, flow, gx, gz, ws)
     raise KeyError(name)
 
 
