@@ -212,7 +212,10 @@ def roofline_block(calls, step_ms, device, n_steps_recorded):
             "bytes_per_launch": dom["bytes_per_launch"], "overhead_bytes": dom["overhead_bytes"], "ms_per_launch": dom["cold_ms"],
             "shape": dom["shape"],
             "how": "dominant = largest time per step over ALL hand-written kernels; shown: its largest launch. bytes = SURVEY "
-                   "§8(d) formulas (frame mix: T-frame tensor read + written once; weight gradients: x and gy read once); "
+                   "§8(d) formulas (frame mix: T-frame tensor read + written once; weight gradients: x and gy read once; "
+                   "lerp+concat launches with shape.act = 1 also carry the decoder block's LeakyReLU pass, reference "
+                   "models/SMOW_Net.py:137: + 8*Cd*hw*s forward (z read, activated half written — it replaces BOTH the "
+                   "reference's activation kernel and the copy of the decoder half), + 12*Cd*hw*s backward); "
                    "time = median of CUDA-graph replays of the C-ABI call on fresh operands rotating over >= 1 GiB "
                    "(HBM-cold, no launch gaps), events on the replay stream; overhead_bytes = non-algorithmic traffic of the "
                    "same launch (e.g. the copy of the decoder half); warm = one operand set (L2-resident when it fits)",

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SMOW_ABI_VERSION 6
+#define SMOW_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define SMOW_API __attribute__((visibility("default")))
@@ -141,6 +141,20 @@ SMOW_API int smow_tlerp_cat_bwd(const void* gcat, void* gskip,
 SMOW_API int smow_tlerp_pair_cat_bwd(const void* gcat, void* gskip_t1, void* gskip_t2,
                             int B, int Cd, int Cs, int64_t hw,
                             int dtype, int layout, void* stream);
+
+/* ---- A3+A4 with the decoder block's LeakyReLU folded in: NO copy of the decoder half ------------------------------------
+ * The decoder half of every concat is the output of conv_trans_block_3d, whose last two operations are BatchNorm and
+ * LeakyReLU(0.2) (models/SMOW_Net.py:136-137, models/SMOW_Net_LW.py:134-135).  Taking the BatchNorm output z instead,
+ *   cat[:, :Cd]      = leaky_relu(z, slope)            (the activation pass the reference runs as its own kernel)
+ *   cat[:, Cd:Cd+Cs] = [T1, (1-l)T1+l*T2, (1-m)T1+m*T2, T2]
+ * one launch writes the whole concat buffer: the stand-alone LeakyReLU pass and the copy of smow_tlerp_cat_fwd are gone.
+ * NDHWC only; skip frames as two pointers, `skip_pair_stride` elements between consecutive pairs (Cs*hw for separate
+ * (B,Cs,h,w) tensors, 2*Cs*hw with skip_t2 = skip_t1 + Cs*hw for a stacked (B,Cs,2,h,w) tensor).
+ * Backward: gz = gcat[:, :Cd] * (z > 0 ? 1 : slope) written dense, gskip as smow_tlerp_cat_bwd — one launch.        */
+SMOW_API int smow_act_tlerp_cat_fwd(const void* z, const void* skip_t1, const void* skip_t2, void* cat,
+                       int B, int Cd, int Cs, int64_t hw, int64_t skip_pair_stride, float slope, int dtype, void* stream);
+SMOW_API int smow_act_tlerp_cat_bwd(const void* gcat, const void* z, void* gz, void* gskip_t1, void* gskip_t2,
+                       int B, int Cd, int Cs, int64_t hw, int64_t skip_pair_stride, float slope, int dtype, void* stream);
 
 /* ---- N2: semantic tokenizer (the sole consumer of the warped stack) ---------------------------
  * Replaces, per frame k of the stack, models/SMOW_Net.py:176-187 (= models/SMOW_Net_LW.py:195-206):

@@ -168,11 +168,24 @@ tlerp_cat_bwd_kernel(const T* __restrict__ gcat, T* __restrict__ g1, T* __restri
 // bytes of cat (the dec part, then the lerped skip part of the same pixel), so every 32-byte sector is completed
 // by one warp even when Cd*sizeof(T) is not a multiple of 32 (SMOW_Net_LW's 28+16 channel level).  The skip
 // vectors are re-read once per slot (4x, from L2/L1 — they are a small fraction of the concat).
+// LeakyReLU of the decoder half, fused into its copy (slope == 1: a plain bit-exact copy)
+template <typename T>
+__device__ __forceinline__ Vec<T> leaky_vec(Vec<T> v, float slope) {
+  if (slope != 1.f) {
+#pragma unroll
+    for (int j = 0; j < Vec<T>::N; ++j) {
+      const float f = cvtf<T>(v.v[j]);
+      v.v[j] = fromf<T>(f > 0.f ? f : f * slope);
+    }
+  }
+  return v;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, const T* __restrict__ s2,
                            int64_t sB, T* __restrict__ cat, int Cd, int Cs, int64_t hw, int64_t n_items,
-                           bool do_copy, bool do_lerp, FastDiv fqt, FastDiv fhw) {
+                           bool do_copy, bool do_lerp, FastDiv fqt, FastDiv fhw, float slope) {
   constexpr int V = Vec<T>::N;
   const int Ct = Cd + Cs;
   const int64_t qd = Cd / V, qt = Ct / V;
@@ -185,7 +198,7 @@ tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, 
       fast_split(i, fqt, r, vt);               // r = (b*4 + slot)*hw + p
       T* dst = cat + ((int64_t)i * V);         // = cat + r*Ct + vt*V: the output is written densely
       if (vt < uqd) {
-        if (do_copy) stv(dst, ldv_stream(dec + ((int64_t)r * Cd + vt * V)));
+        if (do_copy) stv(dst, leaky_vec(ldv_stream(dec + ((int64_t)r * Cd + vt * V)), slope));
         continue;
       }
       if (!do_lerp) continue;
@@ -210,7 +223,7 @@ tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, 
     int64_t r, vt;
     split_index(i, qt, small, r, vt);          // r = (b*4 + slot)*hw + p
     if (vt < qd) {
-      if (do_copy) stv(cat + r * Ct + vt * V, ldv_stream(dec + r * Cd + vt * V));
+      if (do_copy) stv(cat + r * Ct + vt * V, leaky_vec(ldv_stream(dec + r * Cd + vt * V), slope));
       continue;
     }
     if (!do_lerp) continue;
@@ -242,6 +255,62 @@ tlerp_cat_bwd_ndhwc_kernel(const T* __restrict__ gcat, T* __restrict__ g1, T* __
   const int64_t qs = Cs / V, fs = hw * Ct;
   const bool small = n < (1ll << 31) && (int64_t)4 * hw * Ct < (1ll << 31);
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    int64_t bp, vs, b, p;
+    if (small) {
+      uint32_t ubp, uvs, ub, up;
+      fast_split((uint32_t)i, fqs, ubp, uvs);
+      fast_split(ubp, fhw, ub, up);
+      bp = ubp; vs = uvs; b = ub; p = up;
+    } else {
+      split_index(i, qs, false, bp, vs);
+      split_index(bp, hw, false, b, p);
+    }
+    const T* g = gcat + ((b * 4) * hw + p) * Ct + Cd + vs * V;
+    const Vec<T> a = ldv_stream(g), m1 = ldv_stream(g + fs), m2 = ldv_stream(g + 2 * fs), d = ldv_stream(g + 3 * fs);
+    Vec<T> r1, r2;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float f0 = cvtf<T>(a.v[j]), f1 = cvtf<T>(m1.v[j]), f2 = cvtf<T>(m2.v[j]), f3 = cvtf<T>(d.v[j]);
+      r1.v[j] = fromf<T>(fmaf(lw.a2, f2, fmaf(lw.a1, f1, f0)));
+      r2.v[j] = fromf<T>(__fadd_rn(fmaf(lw.b2, f2, __fmul_rn(lw.b1, f1)), f3));
+    }
+    stv(g1 + b * sB + p * Cs + vs * V, r1);
+    stv(g2 + b * sB + p * Cs + vs * V, r2);
+  }
+}
+
+// Backward of the fused activation + lerp + concat: blocks [0, nb_dec) turn the decoder half of the incoming gradient into
+// d z = g * (z > 0 ? 1 : slope) (dense, one 16-byte vector per thread), the remaining blocks are the lerp backward above.
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_tlerp_cat_bwd_ndhwc_kernel(const T* __restrict__ gcat, const T* __restrict__ z, T* __restrict__ gz, T* __restrict__ g1,
+                               T* __restrict__ g2, int64_t sB, int Cd, int Cs, int64_t hw, int64_t n_dec, int64_t n_skip,
+                               int nb_dec, FastDiv fqd, FastDiv fqs, FastDiv fhw, float slope) {
+  constexpr int V = Vec<T>::N;
+  const int Ct = Cd + Cs;
+  if ((int)blockIdx.x < nb_dec) {
+    const int64_t qd = Cd / V;
+    const bool small = n_dec < (1ll << 31);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_dec; i += (int64_t)nb_dec * 256) {
+      int64_t r, v;
+      if (small) { uint32_t ur, uv; fast_split((uint32_t)i, fqd, ur, uv); r = ur; v = uv; }
+      else split_index(i, qd, false, r, v);
+      const Vec<T> g = ldv_stream(gcat + r * Ct + v * V), zz = ldv_stream(z + i * V);
+      Vec<T> o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float gg = cvtf<T>(g.v[j]);
+        o.v[j] = fromf<T>(cvtf<T>(zz.v[j]) > 0.f ? gg : gg * slope);
+      }
+      stv(gz + i * V, o);
+    }
+    return;
+  }
+  const LerpW lw = lerp_weights();
+  const int64_t qs = Cs / V, fs = hw * Ct;
+  const int nb = gridDim.x - nb_dec;
+  const bool small = n_skip < (1ll << 31) && (int64_t)4 * hw * Ct < (1ll << 31);
+  for (int64_t i = (int64_t)(blockIdx.x - nb_dec) * 256 + threadIdx.x; i < n_skip; i += (int64_t)nb * 256) {
     int64_t bp, vs, b, p;
     if (small) {
       uint32_t ubp, uvs, ub, up;
@@ -310,7 +379,7 @@ static int bwd_impl(const T* gcat, T* g1, T* g2, int64_t sB, int64_t sC, int B, 
 
 template <typename T>
 static int fwd_ndhwc(const T* dec, const T* s1, const T* s2, int64_t sB, T* cat, int B, int Cd, int Cs, int64_t hw,
-                     cudaStream_t st) {
+                     cudaStream_t st, float slope = 1.f) {
   constexpr int V = Vec<T>::N;
   const bool do_lerp = s1 != nullptr, do_copy = dec != nullptr && Cd > 0;
   if (!do_lerp && !do_copy) return 0;
@@ -321,9 +390,26 @@ static int fwd_ndhwc(const T* dec, const T* s1, const T* s2, int64_t sB, T* cat,
   const int cap = device_info().sms * 8;
   const int nb = (int)((n_items + 255) / 256 < cap ? (n_items + 255) / 256 : cap);
   tlerp_cat_fwd_ndhwc_kernel<T><<<nb, 256, 0, st>>>(dec, s1, s2, sB, cat, Cd, Cs, hw, n_items, do_copy, do_lerp,
-                                                    make_fastdiv((Cd + Cs) / V), make_fastdiv(hw));
+                                                    make_fastdiv((Cd + Cs) / V), make_fastdiv(hw), slope);
   count_launch();
   return check_launch("tlerp_cat_fwd (NDHWC)");
+}
+
+template <typename T>
+static int act_bwd_ndhwc(const T* gcat, const T* z, T* gz, T* g1, T* g2, int64_t sB, int B, int Cd, int Cs, int64_t hw,
+                         float slope, cudaStream_t st) {
+  constexpr int V = Vec<T>::N;
+  if (Cd <= 0 || Cd % V || Cs % V || !aligned16(gcat) || !aligned16(z) || !aligned16(gz) || !aligned16(g1) || !aligned16(g2) || sB % V)
+    return fail(SMOW_EALIGN, "act_tlerp_cat NDHWC needs Cd > 0, Cd and Cs multiples of %d and 16 B aligned tensors", V);
+  const int64_t n_dec = (int64_t)B * 4 * hw * (Cd / V), n_skip = (int64_t)B * hw * (Cs / V);
+  const int cap = device_info().sms * 8;
+  const int nb_dec = (int)((n_dec + 255) / 256 < cap ? (n_dec + 255) / 256 : cap);
+  const int nb_skip = (int)((n_skip + 255) / 256 < cap ? (n_skip + 255) / 256 : cap);
+  act_tlerp_cat_bwd_ndhwc_kernel<T><<<nb_dec + nb_skip, 256, 0, st>>>(gcat, z, gz, g1, g2, sB, Cd, Cs, hw, n_dec, n_skip, nb_dec,
+                                                                       make_fastdiv(Cd / V), make_fastdiv(Cs / V),
+                                                                       make_fastdiv(hw), slope);
+  count_launch();
+  return check_launch("act_tlerp_cat_bwd (NDHWC)");
 }
 
 template <typename T>
@@ -393,6 +479,30 @@ int smow_tlerp_cat_fwd(const void* dec, const void* skip, void* cat, int B, int 
   const __nv_bfloat16* s = (const __nv_bfloat16*)skip;
   return fwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dec, s, s ? s + hw : nullptr, 2 * Cs * hw, 2 * hw,
                                  (__nv_bfloat16*)cat, B, Cd, Cs, hw, st);
+}
+
+int smow_act_tlerp_cat_fwd(const void* z, const void* skip_t1, const void* skip_t2, void* cat, int B, int Cd, int Cs,
+                           int64_t hw, int64_t skip_pair_stride, float slope, int dtype, void* stream) {
+  if (int e = check_args(cat, B, Cd, Cs, hw, dtype, SMOW_NDHWC)) return e;
+  if (!z || !skip_t1 || !skip_t2 || Cd <= 0) return fail(SMOW_EINVAL, "act_tlerp_cat: null pointer / Cd == 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMOW_F32)
+    return fwd_ndhwc<float>((const float*)z, (const float*)skip_t1, (const float*)skip_t2, skip_pair_stride, (float*)cat, B, Cd,
+                            Cs, hw, st, slope);
+  return fwd_ndhwc<__nv_bfloat16>((const __nv_bfloat16*)z, (const __nv_bfloat16*)skip_t1, (const __nv_bfloat16*)skip_t2,
+                                  skip_pair_stride, (__nv_bfloat16*)cat, B, Cd, Cs, hw, st, slope);
+}
+
+int smow_act_tlerp_cat_bwd(const void* gcat, const void* z, void* gz, void* gskip_t1, void* gskip_t2, int B, int Cd, int Cs,
+                           int64_t hw, int64_t skip_pair_stride, float slope, int dtype, void* stream) {
+  if (int e = check_args(gcat, B, Cd, Cs, hw, dtype, SMOW_NDHWC)) return e;
+  if (!z || !gz || !gskip_t1 || !gskip_t2) return fail(SMOW_EINVAL, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMOW_F32)
+    return act_bwd_ndhwc<float>((const float*)gcat, (const float*)z, (float*)gz, (float*)gskip_t1, (float*)gskip_t2,
+                                skip_pair_stride, B, Cd, Cs, hw, slope, st);
+  return act_bwd_ndhwc<__nv_bfloat16>((const __nv_bfloat16*)gcat, (const __nv_bfloat16*)z, (__nv_bfloat16*)gz,
+                                      (__nv_bfloat16*)gskip_t1, (__nv_bfloat16*)gskip_t2, skip_pair_stride, B, Cd, Cs, hw, slope, st);
 }
 
 int smow_tlerp_pair_cat_bwd(const void* gcat, void* gskip_t1, void* gskip_t2, int B, int Cd, int Cs, int64_t hw,

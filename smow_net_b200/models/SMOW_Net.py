@@ -56,7 +56,7 @@ class SMOW_Net(nn.Module):
 
         dec = self.MaxPool(ops.tlerp(skips[4]))                # reference :73-75
         for k in (1, 2, 3, 4, 5):
-            up = getattr(self, "C3DT%d" % k)(dec)
-            dec = getattr(self, "C3D%d" % k)(ops.tlerp_cat(up, skips[5 - k]))
+            cat = getattr(self, "C3DT%d" % k).forward_into_concat(dec, skip=skips[5 - k])
+            dec = getattr(self, "C3D%d" % k)(cat)
 
         return self.sigmoid(self.decoder(self.Transformer_Decoder(dec, tokens)))

@@ -59,8 +59,8 @@ class SMOW_Net_LW(nn.Module):
 
         dec = self.MaxPool(ops.tlerp_pair_cat(None, pyr1[4], pyr2[4]))   # reference :71-73
         for k in (1, 2, 3, 4):
-            up = getattr(self, "C3DT%d" % k)(dec)
-            dec = getattr(self, "C3D%d" % k)(ops.tlerp_pair_cat(up, pyr1[5 - k], pyr2[5 - k]))
-        dec = self.C3D5(ops.tlerp_cat(self.C3DT5(dec), x0))
+            cat = getattr(self, "C3DT%d" % k).forward_into_concat(dec, skip_pair=(pyr1[5 - k], pyr2[5 - k]))
+            dec = getattr(self, "C3D%d" % k)(cat)
+        dec = self.C3D5(self.C3DT5.forward_into_concat(dec, skip=x0))
 
         return self.sigmoid(self.decoder(self.Transformer_Decoder(dec, tokens)))

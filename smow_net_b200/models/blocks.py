@@ -195,10 +195,26 @@ class TemporalDeconvMix(nn.Module):
         self.batch = nn.BatchNorm3d(out_dim)
         self.leaky = nn.LeakyReLU(0.2, inplace=True)
 
-    def forward(self, x):
+    def pre_activation(self, x):
+        """Everything but the final LeakyReLU: transposed conv, frame mix, BatchNorm."""
         own = [getattr(self, "conv3d_time_%d" % i) for i in range(1, 5)]
-        y = cyclic_frame_mix(self.conv3d_spatial(x), self.conv3d_time_5, own)
-        return self.leaky(self.batch(y))
+        return self.batch(cyclic_frame_mix(self.conv3d_spatial(x), self.conv3d_time_5, own))
+
+    def forward(self, x):
+        return self.leaky(self.pre_activation(x))
+
+    def forward_into_concat(self, x, skip=None, skip_pair=None):
+        """forward(x) concatenated with the temporally up-sampled skip (rows A3 + A4).  On the GPU the block's LeakyReLU is
+        folded into the launch that writes the concat buffer (ops.act_tlerp_*): no stand-alone activation pass, no copy of
+        the decoder half.  `skip` (B,Cs,2,h,w) or `skip_pair` = two (B,Cs,h,w) frames."""
+        from .. import ops
+        cs = skip.shape[1] if skip is not None else skip_pair[0].shape[1]
+        z = self.pre_activation(x)
+        if ops.act_cat_supported(z, cs):
+            slope = self.leaky.negative_slope
+            return ops.act_tlerp_cat(z, skip, slope) if skip is not None else ops.act_tlerp_pair_cat(z, *skip_pair, slope)
+        y = self.leaky(z)
+        return ops.tlerp_cat(y, skip) if skip is not None else ops.tlerp_pair_cat(y, *skip_pair)
 
 
 class DoubleConv3d(nn.Module):

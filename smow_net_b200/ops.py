@@ -423,6 +423,98 @@ def tlerp_pair_cat(dec, x_t1, x_t2):
     return _TLerpPairCat.apply(dec, x_t1, x_t2)
 
 
+# ----------------------------------------------------------------------------- A3+A4 with the block's LeakyReLU folded in
+def act_cat_bytes(B, Cd, hw, s):
+    """The LeakyReLU pass of the decoder block (reference models/SMOW_Net.py:137), now done by the concat launch:
+    z read once, the decoder half of the concat written once."""
+    return B * 8 * Cd * hw * s
+
+
+def act_cat_bwd_bytes(B, Cd, hw, s):
+    """LeakyReLU backward of the decoder half: its gradient slice and z read once, d z written once."""
+    return B * 12 * Cd * hw * s
+
+
+class _ActTLerpCat(torch.autograd.Function):
+    """cat([leaky_relu(z, slope), tlerp(T1, T2)], 1) in one launch; frames given as two (B,Cs,h,w) tensors or as the two
+    time slices of a stacked channels_last_3d (B,Cs,2,h,w) tensor (`stacked`)."""
+
+    @staticmethod
+    def forward(ctx, z, a, b, slope, stacked):
+        B, Cd, _, h, w = z.shape
+        Cs = a.shape[1]
+        z = z.contiguous(memory_format=torch.channels_last_3d)
+        cat = torch.empty((B, Cd + Cs, 4, h, w), dtype=z.dtype, device=z.device, memory_format=torch.channels_last_3d)
+        pair_stride = (2 if stacked else 1) * Cs * h * w
+        lib = _lib.load()
+        with torch.cuda.device_of(z):
+            _meta(B=B, Cd=Cd, Cs=Cs, hw=h * w, dtype=_dtype_code(z), layout=_lib.NDHWC, pair=0, act=1)
+            _call("tlerp_cat_fwd", tlerp_fwd_bytes(B, Cd, Cs, h * w, z.element_size()) + act_cat_bytes(B, Cd, h * w, z.element_size()),
+                  lib.smow_act_tlerp_cat_fwd,
+                  z.data_ptr(), a.data_ptr(), b.data_ptr(), cat.data_ptr(), B, Cd, Cs, h * w, pair_stride, float(slope),
+                  _dtype_code(z), _stream())
+        ctx.save_for_backward(z)
+        ctx.cfg = (B, Cd, Cs, h, w, float(slope), stacked)
+        return cat
+
+    @staticmethod
+    def backward(ctx, gcat):
+        (z,) = ctx.saved_tensors
+        B, Cd, Cs, h, w, slope, stacked = ctx.cfg
+        gcat = gcat.contiguous(memory_format=torch.channels_last_3d)
+        gz = torch.empty_like(z, memory_format=torch.channels_last_3d)
+        if stacked:
+            gs = torch.empty((B, Cs, 2, h, w), dtype=z.dtype, device=z.device, memory_format=torch.channels_last_3d)
+            ga, gb = gs[:, :, 0], gs[:, :, 1]
+        else:
+            ga = torch.empty((B, Cs, h, w), dtype=z.dtype, device=z.device, memory_format=torch.channels_last)
+            gb = torch.empty_like(ga, memory_format=torch.channels_last)
+        pair_stride = (2 if stacked else 1) * Cs * h * w
+        lib = _lib.load()
+        with torch.cuda.device_of(z):
+            _meta(B=B, Cd=Cd, Cs=Cs, hw=h * w, dtype=_dtype_code(z), layout=_lib.NDHWC, pair=0, act=1)
+            _call("tlerp_cat_bwd", tlerp_bwd_bytes(B, Cs, h * w, z.element_size()) + act_cat_bwd_bytes(B, Cd, h * w, z.element_size()),
+                  lib.smow_act_tlerp_cat_bwd,
+                  gcat.data_ptr(), z.data_ptr(), gz.data_ptr(), ga.data_ptr(), gb.data_ptr(), B, Cd, Cs, h * w, pair_stride,
+                  slope, _dtype_code(z), _stream())
+        return gz, ga, gb, None, None
+
+
+def _act_cat_ok(z, a, b):
+    v = 16 // z.element_size()
+    return (z.is_cuda and z.dim() == 5 and z.shape[2] == 4 and z.shape[0] > 0 and z.dtype in _DTYPES and a.dtype == z.dtype
+            and b.dtype == z.dtype and z.shape[1] % v == 0 and a.shape[1] % v == 0 and tuple(a.shape) == tuple(b.shape)
+            and a.shape[0] == z.shape[0] and tuple(a.shape[-2:]) == tuple(z.shape[-2:]))
+
+
+def act_tlerp_pair_cat(z, x_t1, x_t2, slope=0.2):
+    """``cat([leaky_relu(z, slope), interpolate(stack(x_t1, x_t2), (4,h,w))], 1)`` in ONE launch: z is the decoder block's
+    BatchNorm output (B,Cd,4,h,w); the block's LeakyReLU (reference models/SMOW_Net.py:137) is applied while the decoder half
+    is written into the concat buffer, so neither a stand-alone activation pass nor a copy of the decoder half remains."""
+    _require_cuda(z, x_t1, x_t2)
+    if not _act_cat_ok(z, x_t1, x_t2) or x_t1.dim() != 4:
+        raise RuntimeError("act_tlerp_pair_cat: z (B,Cd,4,h,w) and matching (B,Cs,h,w) frames with channel counts that are "
+                           "multiples of the 16-byte vector, got %s / %s" % (tuple(z.shape), tuple(x_t1.shape)))
+    a = x_t1.contiguous(memory_format=torch.channels_last)
+    b = x_t2.contiguous(memory_format=torch.channels_last)
+    return _ActTLerpCat.apply(z, a, b, slope, False)
+
+
+def act_tlerp_cat(z, skip, slope=0.2):
+    """Same with the two frames stacked: skip (B,Cs,2,h,w)."""
+    _require_cuda(z, skip)
+    if skip.dim() != 5 or skip.shape[2] != 2 or not _act_cat_ok(z, skip[:, :, 0], skip[:, :, 1]):
+        raise RuntimeError("act_tlerp_cat: z (B,Cd,4,h,w) and skip (B,Cs,2,h,w) with channel counts that are multiples of the "
+                           "16-byte vector, got %s / %s" % (tuple(z.shape), tuple(skip.shape)))
+    skip = skip.contiguous(memory_format=torch.channels_last_3d)
+    return _ActTLerpCat.apply(z, skip[:, :, 0], skip[:, :, 1], slope, True)
+
+
+def act_cat_supported(z, cs):
+    v = 16 // z.element_size() if z.dtype in _DTYPES else 0
+    return bool(v) and z.is_cuda and z.dim() == 5 and z.shape[2] == 4 and z.shape[0] > 0 and z.shape[1] % v == 0 and cs % v == 0
+
+
 # ----------------------------------------------------------------------------- N2: semantic tokenizer
 def tokenizer_fwd_bytes(B, C, hw, s=4):
     """Algorithmic bytes: the stack is read once (4 frames), tokens written."""

@@ -59,6 +59,20 @@ def build(name, m, dev, gen, sigma=0.3):
         s = 4 if dt == torch.float32 else 2
         skip = _t((B, Cs, 2, hw, 1), dev, dt, lay, gen)
         cat = _t((B, Cd + Cs, 4, hw, 1), dev, dt, lay, gen)
+        if m.get("act"):       # LeakyReLU of the decoder block folded in: z -> cat[:, :Cd], no copy (ops.act_tlerp_*)
+            z = _t((B, Cd, 4, hw, 1), dev, dt, lay, gen)
+            s2 = skip[:, :, 1]
+            if name == "tlerp_cat_fwd":
+                fn = lambda: _lib.check(lib.smow_act_tlerp_cat_fwd(z.data_ptr(), skip.data_ptr(), s2.data_ptr(), cat.data_ptr(), B, Cd,  # noqa: E731
+                                                                   Cs, hw, 2 * Cs * hw, 0.2, m["dtype"], st()), name)
+                alg = ops.tlerp_fwd_bytes(B, Cd, Cs, hw, s) + ops.act_cat_bytes(B, Cd, hw, s)
+                return fn, alg, alg, (z, skip, cat)
+            gz, gskip = torch.empty_like(z), torch.empty_like(skip)
+            g2 = gskip[:, :, 1]
+            fn = lambda: _lib.check(lib.smow_act_tlerp_cat_bwd(cat.data_ptr(), z.data_ptr(), gz.data_ptr(), gskip.data_ptr(), g2.data_ptr(),  # noqa: E731
+                                                               B, Cd, Cs, hw, 2 * Cs * hw, 0.2, m["dtype"], st()), name)
+            alg = ops.tlerp_bwd_bytes(B, Cs, hw, s) + ops.act_cat_bwd_bytes(B, Cd, hw, s)
+            return fn, alg, alg, (z, cat, gz, gskip)
         if name == "tlerp_cat_fwd":
             dec = _t((B, Cd, 4, hw, 1), dev, dt, lay, gen) if Cd and m.get("copy_dec", True) else None
             fn = lambda: _lib.check(lib.smow_tlerp_cat_fwd(None if dec is None else dec.data_ptr(), skip.data_ptr(),  # noqa: E731

@@ -63,6 +63,12 @@ def use_oracle_ops(monkeypatch):
     monkeypatch.setattr(ops, "tlerp_cat", torch_ref.ref_tlerp_cat)
     monkeypatch.setattr(ops, "tlerp_pair_cat",
                         lambda dec, a, b: torch_ref.ref_tlerp_cat(dec, torch_ref.ref_pair_stack(a, b)))
+    # the fused activation + concat forms: the reference's own LeakyReLU (models/SMOW_Net.py:137), then interpolate + cat
+    leaky = torch.nn.functional.leaky_relu
+    monkeypatch.setattr(ops, "act_tlerp_cat", lambda z, skip, slope=0.2: torch_ref.ref_tlerp_cat(leaky(z, slope), skip))
+    monkeypatch.setattr(ops, "act_tlerp_pair_cat",
+                        lambda z, a, b, slope=0.2: torch_ref.ref_tlerp_cat(leaky(z, slope), torch_ref.ref_pair_stack(a, b)))
+    monkeypatch.setattr(ops, "act_cat_supported", lambda z, cs: True)
     # rows N2 / N4: the tokenizer and the cyclic frame mix go to the reference's op sequence too, so a module-level
     # comparison never has the CUDA kernels of those rows in both arms
     from smow_net_b200.models import blocks

@@ -507,3 +507,38 @@ def test_flow_head_is_deterministic_and_refuses_cpu():
     assert all(torch.equal(a, b) for a, b in zip(*outs))
     with pytest.raises(RuntimeError):
         ops.flow_head(x.cpu(), coarse.cpu(), weight.cpu())
+
+
+# ------------------------------------------------------------------------------------------------ A3+A4 with the LeakyReLU folded in
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", [(2, 28, 16, 40, 36, True), (3, 32, 24, 9, 7, False), (1, 320, 96, 8, 8, False), (2, 64, 32, 64, 64, True)])
+def test_act_tlerp_cat_matches_the_reference_sequence(case, dtype):
+    """ops.act_tlerp_cat / act_tlerp_pair_cat = the reference's LeakyReLU(0.2) (models/SMOW_Net.py:137), trilinear 2 -> 4
+    (:64-73) and torch.cat (:78-94) in one launch, against that very ATen sequence on the same device: forward bit-exact
+    in fp32 for the activation half and frames 0 / 3, <= 1e-6 for the lerped frames; gradients <= 1e-6 (fp32) / 2e-2 (bf16)."""
+    import torch.nn.functional as F
+    B, Cd, Cs, h, w, stacked = case
+    if dtype == torch.bfloat16 and (Cd % 8 or Cs % 8):
+        pytest.skip("bf16 vectors hold 8 channels: the modules fall back to the un-fused pair for such channel counts")
+    g = torch.Generator().manual_seed(Cd + Cs)
+    z = torch.randn(B, Cd, 4, h, w, generator=g).to(DEV, dtype).contiguous(memory_format=torch.channels_last_3d)
+    skip = torch.randn(B, Cs, 2, h, w, generator=g).to(DEV, dtype).contiguous(memory_format=torch.channels_last_3d)
+    gcat = torch.randn(B, Cd + Cs, 4, h, w, generator=g).to(DEV, dtype)
+    zi, si = z.clone(memory_format=torch.preserve_format).requires_grad_(True), skip.clone(memory_format=torch.preserve_format).requires_grad_(True)
+    before = _lib.launch_count()
+    if stacked:
+        cat = ops.act_tlerp_cat(zi, si, 0.2)
+    else:
+        cat = ops.act_tlerp_pair_cat(zi, si[:, :, 0], si[:, :, 1], 0.2)
+    cat.backward(gcat)
+    assert _lib.launch_count() - before == 2                          # ONE launch forward, ONE backward
+    zr, sr = z.float().clone().requires_grad_(True), skip.float().clone().requires_grad_(True)
+    want = torch_ref.ref_tlerp_cat(F.leaky_relu(zr, 0.2), sr)
+    want.backward(gcat.float())
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    if dtype == torch.float32:
+        assert torch.equal(cat[:, :Cd], want[:, :Cd]) and torch.equal(cat[:, Cd:, 0], want[:, Cd:, 0]) and torch.equal(cat[:, Cd:, 3], want[:, Cd:, 3])
+    assert float((cat.float() - want).abs().max()) <= tol
+    assert float((zi.grad.float() - zr.grad).abs().max()) <= tol * _scale(zr.grad)
+    assert float((si.grad.float() - sr.grad).abs().max()) <= tol * _scale(sr.grad)
+    assert cat.is_contiguous(memory_format=torch.channels_last_3d)
