@@ -623,6 +623,239 @@ warp_bwd_ndhwc_far_kernel(const float* __restrict__ gout, int64_t sB, const floa
   }
 }
 
+// ---- bf16 storage: the same single-pass tile gather with 8-channel vectors -------------------------------------------
+// Features and gradients are bf16 in HBM (half the bytes), every sum runs in fp32: the staged warped-slot gradient
+// tile holds raw bf16 (16 bytes = 8 channels per unit), phase 2 widens to fp32 registers, accumulates the pass-through
+// slot + the 3x3 probe in fp32 and rounds ONCE on the way out.  Coordinates, probe weights and the flow gradient are
+// the fp32 code of the kernel above.  Far taps are added by bf16x2 reductions (each rounds to bf16: fine at 2e-2).
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
+__global__ void __launch_bounds__(256, 2)
+warp_bwd_ndhwc_tile_bf16_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16* __restrict__ x1,
+                                const __nv_bfloat16* __restrict__ x2, int64_t sB, const float* __restrict__ flow,
+                                const float* __restrict__ xs, const float* __restrict__ ys, __nv_bfloat16* __restrict__ gx1,
+                                __nv_bfloat16* __restrict__ gx2, float* __restrict__ gflow, int C, int H, int W, int lshift,
+                                int R, int tiles_x, int tiles_y, int wshift, int hshift, int* __restrict__ far_flag, int epoch) {
+  extern __shared__ float4 smem4[];
+  const int LC = 1 << lshift;                               // lanes per pixel = min(C/8, 8)
+  const int nchunks = (C >> 3) >> lshift;                    // chunks of LC*8 channels
+  const int HW = H * W;
+  uint4* gws = reinterpret_cast<uint4*>(smem4);             // [(R+2)][34][LC] staged warped-slot gradient (raw bf16)
+  float4* sc = smem4 + (R + 2) * TILE_W2 * LC;              // [(R+2)][34]     source coordinates
+  float4* wt = sc + (R + 2) * TILE_W2;                      // [R*32][3]       probe weights
+  float2* gacc = reinterpret_cast<float2*>(wt + R * TILE_W * 3);
+  int bid = blockIdx.x;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int ty = bid % tiles_y;
+  const int bt = bid / tiles_y;
+  const int h0 = ty * R, w0 = tx * TILE_W;
+  const int b = bt >> 1, t = bt & 1;
+  const int64_t fbase = ((int64_t)(b * 2) * 2 + t) * HW;
+  const __nv_bfloat16* gw = gout + ((int64_t)(b * 4 + 1 + t) * HW) * C;
+  const int n_stage = ((R + 2) * TILE_W2) << lshift;
+  const int adv = 256 >> lshift, adv_r = adv / TILE_W2, adv_c = adv - adv_r * TILE_W2;
+  auto stage = [&](int chunk) {
+    const int sp0 = threadIdx.x >> lshift, lv = threadIdx.x & (LC - 1);
+    int r = sp0 / TILE_W2, c = sp0 - r * TILE_W2;
+    const __nv_bfloat16* g0 = gw + ((chunk << lshift) + lv) * 8;
+    for (int i = threadIdx.x; i < n_stage; i += 256) {
+      const int h = h0 - 1 + r, w = w0 - 1 + c;
+      const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+      cp_async16_zfill(gws + i, g0 + (ok ? (h * W + w) * C : 0), ok);
+      r += adv_r; c += adv_c;
+      if (c >= TILE_W2) { c -= TILE_W2; ++r; }
+    }
+    cp_async_commit();
+  };
+  stage(0);
+  bool found_far = false;
+  {
+    const float* fxp = flow + fbase;
+    const float* fyp = fxp + 2 * (int64_t)HW;
+    const float half_w = __fmul_rn((float)(W - 1), 0.5f), half_h = __fmul_rn((float)(H - 1), 0.5f);
+    for (int s = threadIdx.x; s < (R + 2) * TILE_W2; s += 256) {
+      const int r = s / TILE_W2;
+      const int w = w0 - 1 + s - r * TILE_W2, h = h0 - 1 + r;
+      float4 c = make_float4(-4.f, -4.f, 0.f, 0.f);
+      if (h >= 0 && h < H && w >= 0 && w < W) {
+        const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(fxp + h * W + w), __ldg(fyp + h * W + w), W, H);
+        c.x = __fadd_rn((float)fp.x0, fp.wx1);
+        c.y = __fadd_rn((float)fp.y0, fp.wy1);
+        c.z = __fmul_rn(fp.gx_gate, half_w);
+        c.w = __fmul_rn(fp.gy_gate, half_h);
+        if (far_flag != nullptr && far_tap_mask(fp, w, h) != 0) found_far = true;
+      }
+      sc[s] = c;
+    }
+  }
+  if (found_far) *far_flag = epoch;
+  __syncthreads();
+  for (int pl = threadIdx.x; pl < R * TILE_W; pl += 256) {
+    const int hl = pl >> 5, wl = pl & 31;
+    const float pxf = (float)(w0 + wl), pyf = (float)(h0 + hl);
+    const float pxp = pxf + 1.f, pxm = pxf - 1.f, pyp = pyf + 1.f, pym = pyf - 1.f;
+    float wv[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const float4* row = sc + (hl + dy) * TILE_W2 + wl;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float2 c = *reinterpret_cast<const float2*>(row + dx);
+        const float wx = cover_weight(c.x, pxf, pxp, pxm), wy = cover_weight(c.y, pyf, pyp, pym);
+        wv[dy * 3 + dx] = (wx > 0.f && wy > 0.f) ? __fmul_rn(wx, wy) : 0.f;
+      }
+    }
+    wt[pl * 3 + 0] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    wt[pl * 3 + 1] = make_float4(wv[4], wv[5], wv[6], wv[7]);
+    wt[pl * 3 + 2] = make_float4(wv[8], 0.f, 0.f, 0.f);
+    gacc[pl] = make_float2(0.f, 0.f);
+  }
+  const int n_items = (R * TILE_W) << lshift;
+  const int rowC = W * C;
+  const __nv_bfloat16* gpass = gout + ((int64_t)(b * 4 + (t ? 3 : 0)) * HW) * C;
+  const __nv_bfloat16* src = (t ? x2 : x1) + b * sB;
+  __nv_bfloat16* dst = (t ? gx2 : gx1) + b * sB;
+  const float inv_w = 1.f / (float)W, inv_h = 1.f / (float)H;
+  const int rstride = TILE_W2 * LC;
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    if (chunk > 0) { __syncthreads(); stage(chunk); }
+    cp_async_wait_all();
+    __syncthreads();
+    const int cbase = (chunk << lshift) * 8;
+    for (int base = 0; base < n_items; base += 256) {
+      const int it = base + threadIdx.x;
+      const int pl = it >> lshift, lv = it & (LC - 1);
+      const int hl = pl >> 5, wl = pl & 31;
+      const int h = h0 + hl, w = w0 + wl;
+      const bool live = it < n_items && h < H && w < W;
+      float gix = 0.f, giy = 0.f;
+      float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        const float4 wa = wt[pl * 3], wb = wt[pl * 3 + 1];
+        const float w8 = wt[pl * 3 + 2].x;
+        own = sc[(hl + 1) * TILE_W2 + wl + 1];
+        const float x0f = floorf(own.x), y0f = floorf(own.y);
+        const int x0 = (int)x0f, y0 = (int)y0f;
+        const float wx0 = __fsub_rn(__fadd_rn(x0f, 1.f), own.x), wx1 = __fsub_rn(own.x, x0f);
+        const float wy0 = __fsub_rn(__fadd_rn(y0f, 1.f), own.y), wy1 = __fsub_rn(own.y, y0f);
+        const bool x1ok = x0 + 1 <= W - 1, y1ok = y0 + 1 <= H - 1;
+        const int eo = (h * W + w) * C + cbase + lv * 8;
+        const __nv_bfloat16* xp = src + ((y0 * W + x0) * C + cbase + lv * 8);
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 pass = __ldg(reinterpret_cast<const uint4*>(gpass + eo));
+        const uint4 xa = __ldg(reinterpret_cast<const uint4*>(xp));
+        const uint4 xb = x1ok ? __ldg(reinterpret_cast<const uint4*>(xp + C)) : z4;
+        const uint4 xc = y1ok ? __ldg(reinterpret_cast<const uint4*>(xp + rowC)) : z4;
+        const uint4 xd = (x1ok && y1ok) ? __ldg(reinterpret_cast<const uint4*>(xp + rowC + C)) : z4;
+        const uint4* gc = gws + ((hl + 1) * TILE_W2 + wl + 1) * LC + lv;
+        const float wgt[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, w8};
+        float g[8], sum[8], tmp[8];
+        unpack8(gc[0], g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum[k] = wgt[4] * g[k];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          if (j != 4 && wgt[j] != 0.f) {
+            unpack8(gc[(j / 3 - 1) * rstride + (j % 3 - 1) * LC], tmp);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum[k] = fmaf(wgt[j], tmp[k], sum[k]);
+          }
+        }
+        unpack8(pass, tmp);
+        Pack<__nv_bfloat16> o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.f[k] = __fadd_rn(tmp[k], sum[k]);
+        st_pack<__nv_bfloat16>(dst + eo, o);
+        auto tap = [&](const uint4& xv, float dgx, float dgy) {
+          unpack8(xv, tmp);
+          float dot = __fmul_rn(tmp[0], g[0]);
+#pragma unroll
+          for (int k = 1; k < 8; ++k) dot = fmaf(tmp[k], g[k], dot);
+          gix = fmaf(dgx, dot, gix);
+          giy = fmaf(dgy, dot, giy);
+        };
+        tap(xa, -wy0, -wx0);
+        tap(xb, wy0, -wx1);
+        tap(xc, -wy1, wx0);
+        tap(xd, wy1, wx1);
+      }
+      for (int d = LC >> 1; d > 0; d >>= 1) {
+        gix += __shfl_xor_sync(0xffffffffu, gix, d);
+        giy += __shfl_xor_sync(0xffffffffu, giy, d);
+      }
+      if (live && lv == 0) {
+        if (nchunks > 1) {
+          const float2 a = gacc[pl];
+          gix += a.x; giy += a.y;
+          gacc[pl] = make_float2(gix, giy);
+        }
+        if (chunk == nchunks - 1) {
+          const float a = __fmul_rn(own.z, gix), c = __fmul_rn(own.w, giy);
+          float* gf = gflow + fbase + h * W + w;
+          gf[0] = wshift >= 0 ? __fmul_rn(a, inv_w) : __fdiv_rn(a, (float)W);
+          gf[2 * (int64_t)HW] = hshift >= 0 ? __fmul_rn(c, inv_h) : __fdiv_rn(c, (float)H);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+warp_bwd_ndhwc_far_bf16_kernel(const __nv_bfloat16* __restrict__ gout, int64_t sB, const float* __restrict__ flow,
+                               const float* __restrict__ xs, const float* __restrict__ ys, __nv_bfloat16* __restrict__ gx1,
+                               __nv_bfloat16* __restrict__ gx2, int C, int H, int W, int q, int planes,
+                               const int* __restrict__ far_flag, int epoch) {
+  if (far_flag != nullptr && *far_flag != epoch) return;
+  const int HW = H * W;
+  const int64_t total = (int64_t)HW * planes, stride = (int64_t)gridDim.x * 256;
+  const int64_t rounds = (total + stride - 1) / stride;
+  const int lane = threadIdx.x & 31;
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (int64_t r = 0; r < rounds; ++r, i += stride) {
+    int mask = 0, bt = 0, p = 0, o_nw = 0;
+    float wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f;
+    if (i < total) {
+      bt = (int)(i / HW);
+      p = (int)(i - (int64_t)bt * HW);
+      const int h = p / W, w = p - h * W;
+      const int64_t fo = ((int64_t)(bt >> 1) * 4 + (bt & 1)) * HW + p;
+      const Footprint fp = footprint_auto(__ldg(xs + w), __ldg(ys + h), __ldg(flow + fo), __ldg(flow + fo + 2 * (int64_t)HW), W, H);
+      wx0 = fp.wx0; wx1 = fp.wx1; wy0 = fp.wy0; wy1 = fp.wy1;
+      o_nw = fp.y0 * W + fp.x0;
+      mask = far_tap_mask(fp, w, h);
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, mask != 0);
+    while (todo) {
+      const int sl = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int m = __shfl_sync(0xffffffffu, mask, sl), sbt = __shfl_sync(0xffffffffu, bt, sl);
+      const int sp = __shfl_sync(0xffffffffu, p, sl), so = __shfl_sync(0xffffffffu, o_nw, sl);
+      const float a0 = __shfl_sync(0xffffffffu, wx0, sl), a1 = __shfl_sync(0xffffffffu, wx1, sl);
+      const float b0 = __shfl_sync(0xffffffffu, wy0, sl), b1 = __shfl_sync(0xffffffffu, wy1, sl);
+      const int b = sbt >> 1, t = sbt & 1;
+      const __nv_bfloat16* gwp = gout + ((int64_t)(b * 4 + 1 + t) * HW + sp) * C;
+      __nv_bfloat16* dst = (t ? gx2 : gx1) + b * sB;
+      for (int v = lane; v < q; v += 32) {
+        float g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(gwp + v * 8)), g);
+        auto add = [&](int off, float wgt) {
+          __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(dst + (int64_t)off * C + v * 8);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) atomicAdd(d2 + k, __floats2bfloat162_rn(wgt * g[2 * k], wgt * g[2 * k + 1]));
+        };
+        if (m & 1) add(so, __fmul_rn(a0, b0));
+        if (m & 2) add(so + 1, __fmul_rn(a1, b0));
+        if (m & 4) add(so + W, __fmul_rn(a0, b1));
+        if (m & 8) add(so + W + 1, __fmul_rn(a1, b1));
+      }
+    }
+  }
+}
+
 // ---- (S) vector-atomic scatter; both kernels are grid-stride over (plane, item) so that the "other family did
 // the work" exit costs a few hundred blocks, not one block per 256 items ----
 template <typename T>
@@ -749,7 +982,34 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
                    const float* ys, T* gx1, T* gx2, float* gflow, int B, int C, int H, int W, void* ws,
                    int64_t ws_bytes, cudaStream_t st) {
   if constexpr (!std::is_same<T, float>::value) {
-    return fail(SMOW_EDTYPE, "NDHWC warp backward is built for fp32 only (use the NCDHW layout for bf16)");
+    // bf16 storage: single-pass tile gather with 8-channel vectors + bf16x2 far-tap reductions
+    if (C % 8 || !aligned16(gout) || !aligned16(x1) || !aligned16(x2) || !aligned16(gx1) || !aligned16(gx2) || sB % 8)
+      return fail(SMOW_EALIGN, "NDHWC bf16 warp needs C %% 8 == 0 and 16 B aligned tensors");
+    const int q = C / 8, qs = ilog2_exact(q);
+    const int HW = H * W;
+    if (qs < 0) return fail(SMOW_EDTYPE, "NDHWC bf16 warp backward needs C / 8 to be a power of two (got C = %d)", C);
+    if ((int64_t)HW * C >= (1ll << 31)) return fail(SMOW_ERANGE, "plane too large");
+    const int lshift = qs < 3 ? qs : 3;
+    int R = option(OPT_NDHWC_BWD_ROWS);
+    if (R <= 0) R = lshift == 3 ? 8 : 12;
+    if (R > H) R = H;
+    const size_t smem = tile_smem_bytes(R, 1 << lshift);
+    if (smem > 72 * 1024) return fail(SMOW_ERANGE, "NDHWC bf16 warp backward: tile does not fit shared memory");
+    const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + R - 1) / R;
+    const unsigned tgrid = (unsigned)(tiles_x * tiles_y * 2 * B);
+    static std::atomic<int> g_epoch16{1 << 20};
+    int* far_flag = (ws != nullptr && ws_bytes >= 64 && aligned16(ws)) ? reinterpret_cast<int*>(ws) : nullptr;
+    const int epoch = g_epoch16.fetch_add(1, std::memory_order_relaxed) + 1;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(warp_bwd_ndhwc_tile_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    warp_bwd_ndhwc_tile_bf16_kernel<<<tgrid, 256, smem, st>>>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, C, H, W, lshift, R,
+                                                              tiles_x, tiles_y, ilog2_exact(W), ilog2_exact(H), far_flag, epoch);
+    const int64_t pf = (int64_t)HW * 2 * B;
+    const int fcap = device_info().sms * 4;
+    const int fgrid = (int)((pf + 255) / 256 < fcap ? (pf + 255) / 256 : fcap);
+    warp_bwd_ndhwc_far_bf16_kernel<<<fgrid, 256, 0, st>>>(gout, sB, flow, xs, ys, gx1, gx2, C, H, W, q, 2 * B, far_flag, epoch);
+    count_launch(2);
+    return check_launch("warp_bwd_ndhwc_tile (bf16)");
   } else {
     if (C % 4 || !aligned16(gout) || !aligned16(x1) || !aligned16(x2) || !aligned16(gx1) || !aligned16(gx2) || sB % 4)
       return fail(SMOW_EALIGN, "NDHWC warp needs C %% 4 == 0 and 16 B aligned tensors");

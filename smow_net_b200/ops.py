@@ -62,6 +62,15 @@ def _layout5(t, *channel_counts, ndhwc_ok=True):
     return t.contiguous(), _lib.NCDHW
 
 
+def _ndhwc_warp_ok(t, C):
+    """The NDHWC warp kernels take fp32 (any C % 4 == 0) and bf16 storage with C / 8 a power of two (the tile gather's
+    lanes-per-pixel split); other bf16 channel counts go through the NCDHW kernels."""
+    if t.dtype == torch.float32:
+        return True
+    q = C // 8
+    return t.dtype == torch.bfloat16 and C % 8 == 0 and q > 0 and (q & (q - 1)) == 0
+
+
 def _as_layout(t, layout):
     if layout == _lib.NCDHW:
         return t.contiguous()
@@ -187,9 +196,9 @@ def _bwd_workspace(lib, like, layout, B, H, W):
     """Caller-owned scratch of the NDHWC fp32 backward (the C ABI never allocates): the gather-list variant (3) needs
     per-pixel lists; the default tile gather only a 64-byte word block for its far-tap stamp — zero-initialised once
     and cached per (device, stream), because two launches in flight must not share a stamp."""
-    if layout != _lib.NDHWC or like.dtype != torch.float32:
+    if layout != _lib.NDHWC:
         return None, 0
-    if _lib.get_option("warp_bwd_variant") == 3:
+    if like.dtype == torch.float32 and _lib.get_option("warp_bwd_variant") == 3:
         n = int(lib.smow_warp_bwd_workspace_bytes(B, H, W))
         return torch.empty(n, dtype=torch.uint8, device=like.device), n
     if torch.cuda.is_current_stream_capturing():
@@ -213,7 +222,7 @@ class _WarpStack(torch.autograd.Function):
         B, C, _, H, W = x.shape
         if tuple(flow.shape) != (B, 2, 2, H, W):
             raise RuntimeError("flow_warp: flow must be (B,2,2,H,W)=%s, got %s" % ((B, 2, 2, H, W), tuple(flow.shape)))
-        x, layout = _layout5(x, C, ndhwc_ok=x.dtype == torch.float32)
+        x, layout = _layout5(x, C, ndhwc_ok=_ndhwc_warp_ok(x, C))
         flow = flow.float().contiguous()
         out = _empty((B, C, 4, H, W), x, layout)
         xs, ys = base_grid(W, x.device), base_grid(H, x.device)
@@ -255,7 +264,7 @@ class _WarpPair(torch.autograd.Function):
         B, C, H, W = x1.shape
         if tuple(flow.shape) != (B, 2, 2, H, W):
             raise RuntimeError("warp_pair: flow must be (B,2,2,H,W)")
-        x1, layout = _layout5(x1, C, ndhwc_ok=x1.dtype == torch.float32)
+        x1, layout = _layout5(x1, C, ndhwc_ok=_ndhwc_warp_ok(x1, C))
         x2 = _as_layout(x2, layout)
         flow = flow.float().contiguous()
         out = _empty((B, C, 4, H, W), x1, layout)

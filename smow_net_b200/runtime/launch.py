@@ -62,9 +62,11 @@ def align_pointwise_grad_strides(model):
     gradient into its bucket view.  A tensor hook re-spells the gradient's strides as the parameter's (a view of the same
     memory, no kernel), so gradient_as_bucket_view stays zero-copy."""
     for p in model.parameters():
-        if p.requires_grad and p.dim() >= 4 and all(int(k) == 1 for k in p.shape[2:]):
+        if p.requires_grad and p.dim() >= 4 and any(int(k) == 1 for k in p.shape):
             def fix(g, p=p):
-                if g.stride() != p.stride() and g.is_contiguous():
+                # strides may differ only where the size is 1 (depthwise (C,1,k,k,k) weights, 1x1 kernels): same bytes
+                if g.stride() != p.stride() and g.shape == p.shape and all(
+                        n == 1 or a == b for n, a, b in zip(g.shape, g.stride(), p.stride())):
                     return g.as_strided(g.shape, p.stride(), g.storage_offset())
                 return g
             p.register_hook(fix)
