@@ -565,22 +565,27 @@ mix_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   }
 }
 
-// gw[m][ci][co] = sum over CTAs of part[cta][m][ci][co], in CTA order.  grid (ceil(C*C/256), 1+T), block 256.
+// gw[m][ci][co] = sum over CTAs of part[cta][m][ci][co].  grid (ceil(C*C/32), 1+T), block 256 = 32 elements x 8 CTA slices:
+// every thread adds every 8th partial (independent loads in flight), the 8 slices are then added in a fixed order.
 __global__ void __launch_bounds__(256)
 mix_wgrad_tc_combine_kernel(const float* __restrict__ part, float* __restrict__ gw, int CC, int nm, int nctas) {
-  const int e = blockIdx.x * 256 + threadIdx.x, m = blockIdx.y;
-  if (e >= CC) return;
-  const float* src = part + (size_t)m * CC + e;
-  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-  int c = 0;
-  for (; c + 4 <= nctas; c += 4) {
-    t0 += src[(size_t)(c + 0) * nm * CC];
-    t1 += src[(size_t)(c + 1) * nm * CC];
-    t2 += src[(size_t)(c + 2) * nm * CC];
-    t3 += src[(size_t)(c + 3) * nm * CC];
+  __shared__ float red[8][32];
+  const int el = threadIdx.x & 31, sl = threadIdx.x >> 5, e = blockIdx.x * 32 + el, m = blockIdx.y;
+  float t0 = 0.f, t1 = 0.f;
+  if (e < CC) {
+    const float* src = part + (size_t)m * CC + e;
+    int c = sl;
+    for (; c + 8 < nctas; c += 16) { t0 += src[(size_t)c * nm * CC]; t1 += src[(size_t)(c + 8) * nm * CC]; }
+    if (c < nctas) t0 += src[(size_t)c * nm * CC];
   }
-  for (; c < nctas; ++c) t0 += src[(size_t)c * nm * CC];
-  gw[(size_t)m * CC + e] = (t0 + t1) + (t2 + t3);
+  red[sl][el] = t0 + t1;
+  __syncthreads();
+  if (sl == 0 && e < CC) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += red[k][el];
+    gw[(size_t)m * CC + e] = r;
+  }
 }
 
 // ---- T = 4, C <= 32 (the big decoder levels): the four frames of a 64-pixel tile are stacked along M ---------------------
@@ -681,25 +686,35 @@ mix_wgrad_tc4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   }
 }
 
-// gw[0] = sum over CTAs and slots 0..3; gw[1+g] = sum over CTAs of slot 4+g.  grid (ceil(C*C/256), 5), block 256.
+// gw[0] = sum over CTAs and slots 0..3; gw[1+g] = sum over CTAs of slot 4+g.  grid (ceil(C*C/32), 5), block 256 = 32 elements
+// x 8 CTA slices, fixed-order slice reduction.
 __global__ void __launch_bounds__(256)
 mix_wgrad_tc4_combine_kernel(const float* __restrict__ part, float* __restrict__ gw, int CC, int nctas) {
-  const int e = blockIdx.x * 256 + threadIdx.x, m = blockIdx.y;
-  if (e >= CC) return;
+  __shared__ float red[8][32];
+  const int el = threadIdx.x & 31, sl = threadIdx.x >> 5, e = blockIdx.x * 32 + el, m = blockIdx.y;
   float t0 = 0.f, t1 = 0.f;
-  if (m == 0) {
-    for (int c = 0; c < nctas; ++c) {
-      const float* src = part + (size_t)c * 8 * CC + e;
-      t0 += src[0] + src[(size_t)CC];
-      t1 += src[(size_t)2 * CC] + src[(size_t)3 * CC];
+  if (e < CC) {
+    if (m == 0) {
+      for (int c = sl; c < nctas; c += 8) {
+        const float* src = part + (size_t)c * 8 * CC + e;
+        t0 += src[0] + src[(size_t)CC];
+        t1 += src[(size_t)2 * CC] + src[(size_t)3 * CC];
+      }
+    } else {
+      const float* src = part + (size_t)(3 + m) * CC + e;
+      int c = sl;
+      for (; c + 8 < nctas; c += 16) { t0 += src[(size_t)c * 8 * CC]; t1 += src[(size_t)(c + 8) * 8 * CC]; }
+      if (c < nctas) t0 += src[(size_t)c * 8 * CC];
     }
-  } else {
-    const float* src = part + (size_t)(3 + m) * CC + e;
-    int c = 0;
-    for (; c + 2 <= nctas; c += 2) { t0 += src[(size_t)c * 8 * CC]; t1 += src[(size_t)(c + 1) * 8 * CC]; }
-    for (; c < nctas; ++c) t0 += src[(size_t)c * 8 * CC];
   }
-  gw[(size_t)m * CC + e] = t0 + t1;
+  red[sl][el] = t0 + t1;
+  __syncthreads();
+  if (sl == 0 && e < CC) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += red[k][el];
+    gw[(size_t)m * CC + e] = r;
+  }
 }
 
 static bool wgrad_tc4_ok(int C, int T) { return T == 4 && C >= 16 && C <= 32 && C % 4 == 0 && !(option(OPT_TC_DEBUG) & 64); }
@@ -780,7 +795,7 @@ int smow_frame_mix_wgrad_tc(const float* x, const float* gy, float* gw, int B, i
     const int nctas = wgrad_tc4_ctas(B, hw);
     cudaStream_t st4 = (cudaStream_t)stream;
     mix_wgrad_tc4_kernel<<<nctas, 128, smem4, st4>>>(tm_x, tm_g, q);
-    mix_wgrad_tc4_combine_kernel<<<dim3((C * C + 255) / 256, 5), 256, 0, st4>>>(q.part, gw, C * C, nctas);
+    mix_wgrad_tc4_combine_kernel<<<dim3((C * C + 31) / 32, 5), 256, 0, st4>>>(q.part, gw, C * C, nctas);
     count_launch(2);
     return check_launch("frame_mix_wgrad_tc");
   }
@@ -806,7 +821,7 @@ int smow_frame_mix_wgrad_tc(const float* x, const float* gy, float* gw, int B, i
     return check_launch("frame_mix_wgrad_tc (shared-memory opt-in)");
   cudaStream_t st = (cudaStream_t)stream;
   mix_wgrad_tc_kernel<<<dim3(nctas, mch, nch), 128, smem, st>>>(tm_x, tm_g, p);
-  mix_wgrad_tc_combine_kernel<<<dim3((C * C + 255) / 256, 1 + T), 256, 0, st>>>(p.part, gw, C * C, 1 + T, nctas);
+  mix_wgrad_tc_combine_kernel<<<dim3((C * C + 31) / 32, 1 + T), 256, 0, st>>>(p.part, gw, C * C, 1 + T, nctas);
   count_launch(2);
   return check_launch("frame_mix_wgrad_tc");
 }

@@ -598,18 +598,23 @@ warp_bwd_ndhwc_far_kernel(const float* __restrict__ gout, int64_t sB, const floa
       o_nw = fp.y0 * W + fp.x0;
       mask = far_tap_mask(fp, w, h);
     }
-    unsigned todo = __ballot_sync(0xffffffffu, mask != 0);
-    while (todo) {
-      const int sl = __ffs(todo) - 1;
-      todo &= todo - 1;
+    const unsigned any = __ballot_sync(0xffffffffu, mask != 0);
+    if (any == 0) continue;
+    // the warp serves `nsub` sources at a time: with q = C/4 < 32 channel vectors per pixel, 32/q sources share the lanes
+    const int nsub = q >= 32 ? 1 : 32 / q, qq = q >= 32 ? 32 : q;
+    const int sub = lane / qq, v0 = lane - sub * qq;
+    for (int base = 0; base < 32; base += nsub) {
+      if (((any >> base) & ((nsub == 32 ? 0xffffffffu : ((1u << nsub) - 1u)))) == 0) continue;
+      const int sl = base + sub;
       const int m = __shfl_sync(0xffffffffu, mask, sl), sbt = __shfl_sync(0xffffffffu, bt, sl);
       const int sp = __shfl_sync(0xffffffffu, p, sl), so = __shfl_sync(0xffffffffu, o_nw, sl);
       const float a0 = __shfl_sync(0xffffffffu, wx0, sl), a1 = __shfl_sync(0xffffffffu, wx1, sl);
       const float b0 = __shfl_sync(0xffffffffu, wy0, sl), b1 = __shfl_sync(0xffffffffu, wy1, sl);
+      if (m == 0) continue;
       const int b = sbt >> 1, t = sbt & 1;
       const float* gwp = gout + ((int64_t)(b * 4 + 1 + t) * HW + sp) * C;
       float* dst = (t ? gx2 : gx1) + b * sB;
-      for (int v = lane; v < q; v += 32) {
+      for (int v = v0; v < q; v += 32) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gwp + v * 4));
         auto add = [&](int off, float wgt) {
           atomicAdd(reinterpret_cast<float4*>(dst + (int64_t)off * C + v * 4), make_float4(wgt * g.x, wgt * g.y, wgt * g.z, wgt * g.w));
@@ -828,18 +833,22 @@ warp_bwd_ndhwc_far_bf16_kernel(const __nv_bfloat16* __restrict__ gout, int64_t s
       o_nw = fp.y0 * W + fp.x0;
       mask = far_tap_mask(fp, w, h);
     }
-    unsigned todo = __ballot_sync(0xffffffffu, mask != 0);
-    while (todo) {
-      const int sl = __ffs(todo) - 1;
-      todo &= todo - 1;
+    const unsigned any = __ballot_sync(0xffffffffu, mask != 0);
+    if (any == 0) continue;
+    const int nsub = q >= 32 ? 1 : 32 / q, qq = q >= 32 ? 32 : q;
+    const int sub = lane / qq, v0 = lane - sub * qq;
+    for (int base = 0; base < 32; base += nsub) {
+      if (((any >> base) & ((nsub == 32 ? 0xffffffffu : ((1u << nsub) - 1u)))) == 0) continue;
+      const int sl = base + sub;
       const int m = __shfl_sync(0xffffffffu, mask, sl), sbt = __shfl_sync(0xffffffffu, bt, sl);
       const int sp = __shfl_sync(0xffffffffu, p, sl), so = __shfl_sync(0xffffffffu, o_nw, sl);
       const float a0 = __shfl_sync(0xffffffffu, wx0, sl), a1 = __shfl_sync(0xffffffffu, wx1, sl);
       const float b0 = __shfl_sync(0xffffffffu, wy0, sl), b1 = __shfl_sync(0xffffffffu, wy1, sl);
+      if (m == 0) continue;
       const int b = sbt >> 1, t = sbt & 1;
       const __nv_bfloat16* gwp = gout + ((int64_t)(b * 4 + 1 + t) * HW + sp) * C;
       __nv_bfloat16* dst = (t ? gx2 : gx1) + b * sB;
-      for (int v = lane; v < q; v += 32) {
+      for (int v = v0; v < q; v += 32) {
         float g[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(gwp + v * 8)), g);
         auto add = [&](int off, float wgt) {
