@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""ncu target: every hand-written kernel once (after one warm call) on HBM-cold operands through the C ABI.
+
+    python benchmarks/one_kernel_r2.py            # B = 64, C = 32, 128 x 128 (1 GiB-class tensors) + the bf16 / flow-head shapes
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from smow_net_b200 import _lib, probe
+
+dev = torch.device("cuda:0")
+gen = torch.Generator(device=dev).manual_seed(0)
+B, C, H = 64, 32, 128
+F32, BF16, ND = _lib.F32, _lib.BF16, _lib.NDHWC
+CASES = [
+    ("warp_stack_fwd", {"B": B, "C": C, "H": H, "W": H, "dtype": F32, "layout": ND, "pair": 0}),
+    ("warp_stack_bwd", {"B": B, "C": C, "H": H, "W": H, "dtype": F32, "layout": ND, "pair": 0}),
+    ("warp_stack_fwd", {"B": B, "C": 64, "H": H, "W": H, "dtype": BF16, "layout": ND, "pair": 0}),
+    ("warp_stack_bwd", {"B": B, "C": 64, "H": H, "W": H, "dtype": BF16, "layout": ND, "pair": 0}),
+    ("tlerp_cat_fwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 1}),
+    ("tlerp_cat_bwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 1}),
+    ("tokenizer_fwd", {"B": B, "C": C, "hw": H * H}),
+    ("tokenizer_bwd", {"B": B, "C": C, "hw": H * H}),
+    ("frame_mix_fwd", {"B": B, "C": C, "T": 4, "hw": H * H, "tc": 1}),
+    ("frame_mix_bwd", {"B": B, "C": C, "T": 4, "hw": H * H, "tc": 1}),
+    ("frame_mix_wgrad", {"B": B, "C": C, "T": 4, "hw": H * H, "tc": 1}),
+    ("frame_mix_fwd", {"B": B, "C": 16, "T": 4, "hw": H * H, "tc": 1}),
+    ("frame_mix_wgrad", {"B": B, "C": 16, "T": 4, "hw": H * H, "tc": 1}),
+    ("frame_mix_fwd", {"B": 16, "C": 128, "T": 2, "hw": 64 * 64, "tc": 1}),
+    ("frame_mix_wgrad", {"B": 16, "C": 128, "T": 2, "hw": 64 * 64, "tc": 1}),
+    ("flow_head_fwd", {"B": B, "C": C, "H": H, "W": H, "h": 16, "w": 16}),
+    ("flow_head_bwd", {"B": B, "C": C, "H": H, "W": H, "h": 16, "w": 16}),
+]
+for name, meta in CASES:
+    fn, nbytes, _, keep = probe.build(name, meta, dev, gen)
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print("%-16s %s: %.1f us, %.0f GB/s algorithmic" % (name, {k: v for k, v in meta.items() if k in ("B", "C", "T", "Cd", "Cs", "dtype")},
+                                                        ms * 1e3, nbytes / ms / 1e6), flush=True)
+    del fn, keep
+    torch.cuda.empty_cache()

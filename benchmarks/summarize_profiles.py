@@ -37,6 +37,7 @@ METRICS = [
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
 ]
+OURS = ("warp_", "tlerp_", "act_tlerp_", "tok_", "mix_", "flow_head_")      # kernel-name prefixes of libsmow_b200.so
 TO_BYTES = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 TO_US = {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}
 
@@ -72,12 +73,12 @@ def launches(tag):
         f.write("%d launches, %.1f ms of kernel time in total.\n\n| kernel | launches | us | share |\n|---|---:|---:|---:|\n" % (n, total / 1e3))
         ours = 0.0
         for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            mine = k.startswith(("warp_", "tlerp_", "tok_", "mix_"))
+            mine = k.startswith(OURS)
             ours += us if mine else 0
             if us / total >= 0.003 or mine:
                 f.write("| %s%s | %d | %.1f | %.2f %% |\n" % ("**" if mine else "", k + ("**" if mine else ""), c, us, 100 * us / total))
-        f.write("\nHand-written kernels (rows A1-A5: warp_*, tlerp_*; N2: tok_*; N4: mix_*): %.1f us = %.2f %% of the step's "
-                "kernel time.\n" % (ours, 100 * ours / total))
+        f.write("\nHand-written kernels (rows A1-A5: warp_*, tlerp_*, act_tlerp_*; N1: flow_head_*; N2: tok_*; N4: mix_*): %.1f us = "
+                "%.2f %% of the step's kernel time.\n" % (ours, 100 * ours / total))
 
 
 def ncu_raw(rep):
@@ -110,14 +111,17 @@ def kernels(tag):
         f.write("# %s — `ncu --set full --clock-control none` of the hand-written kernels\n\n" % tag)
         f.write("Raw reports stay in gpurun_out/ (scratch); this file is the committed summary. Durations under ncu are\n"
                 "cold-cache and serialised; CUDA-event timings are in the sweep / bench files.\n")
-        for part, title in (("cold", "HBM-cold: benchmarks/one_kernel.py --C 32 --H 128 --B 64 --layout ndhwc (fp32, 1.07 GB working set)"),
+        cold_title = ("HBM-cold: benchmarks/one_kernel.py --C 32 --H 128 --B 64 --layout ndhwc (fp32, 1.07 GB working set)" if tag == "r1" else
+                      "HBM-cold: benchmarks/one_kernel_r2.py (C-ABI calls on fresh operands, B = 64, C = 32, 128 x 128 unless the row says "
+                      "otherwise; second launch of each)")
+        for part, title in (("cold", cold_title),
                             ("instep", "inside one bench step (SMOW_Net_LW, batch 16; operands partly L2-resident)")):
             rep = os.path.join(OUT, "%s_%s_kernels.ncu-rep" % (tag, part))
             if not os.path.exists(rep):
                 continue
             rows = ncu_raw(rep)
             f.write("\n## %s\n\n| # | kernel | %s |\n|---|---|%s\n" % (title, " | ".join(t for _, t in METRICS), "---:|" * len(METRICS)))
-            rows = [d for d in rows if d["name"].startswith(("warp_", "tlerp_", "tok_", "mix_"))]
+            rows = [d for d in rows if d["name"].startswith(OURS)]
             for i, d in enumerate(rows):
                 cells = []
                 for m, _ in METRICS:
@@ -143,8 +147,9 @@ def kernels(tag):
     if traffic:
         op_of = {"warp_fwd": "warp_stack_fwd", "warp_stack_fwd": "warp_stack_fwd", "warp_bwd": "warp_stack_bwd",
                  "warp_stack_bwd": "warp_stack_bwd", "tlerp_cat_fwd": "tlerp_cat_fwd", "tlerp_cat_bwd": "tlerp_cat_bwd",
-                 "tok_fwd": "tokenizer_fwd", "tok_bwd": "tokenizer_bwd", "mix_apply": "frame_mix_apply",
-                 "mix_wgrad": "frame_mix_wgrad"}
+                 "act_tlerp_cat_bwd": "tlerp_cat_bwd", "tok_fwd": "tokenizer_fwd", "tok_bwd": "tokenizer_bwd",
+                 "mix_apply": "frame_mix_apply", "mix_wgrad": "frame_mix_wgrad", "flow_head_fwd": "flow_head_fwd",
+                 "flow_head_bwd": "flow_head_bwd"}
         per_op = {}
         for k, (n, b, bmax) in traffic.items():
             for pre, op in op_of.items():
@@ -157,6 +162,9 @@ def kernels(tag):
                     break
         res = {op: v["bytes"] / max(1, v["launches"]) for op, v in per_op.items()}
         res.update({op + "@largest": v["largest"] for op, v in per_op.items()})      # the operator's biggest launch
+        if "frame_mix_apply" in res:          # bench.py names the two uses of the apply kernel separately
+            for alias in ("frame_mix_fwd", "frame_mix_bwd"):
+                res[alias], res[alias + "@largest"] = res["frame_mix_apply"], res["frame_mix_apply@largest"]
         res["_source"] = "profiles/%s_ncu_kernels.md (in-step capture), dram__bytes_read+write per C-ABI call" % tag
         json.dump(res, open(os.path.join(PROF, "roofline_traffic.json"), "w"), indent=1)
 
@@ -188,10 +196,55 @@ def sweep(tag):
                 r["op"], r["dtype"], r["Cd"], r["Cs"], r["h"], r["B"], r["variant"], r["ms"], r["gbps"], r["frac"], r["ref_ms"], r["speedup"]))
 
 
+def bench_blocks(tag):
+    """profiles/<tag>_bench.md from gpurun_out/<tag>_bench.log (the builder's own full bench.py run): headline, roofline table,
+    cfg3 / cfg4 / gpu_reference and the configs[4] sweep with its clock record."""
+    p = os.path.join(OUT, tag + "_bench.log")
+    if not os.path.exists(p):
+        return
+    line = [l for l in open(p) if l.startswith("{")]
+    if not line:
+        return
+    d = json.loads(line[-1])
+    with open(os.path.join(PROF, tag + "_bench.md"), "w") as f:
+        f.write("# %s — builder-side `python bench.py` on 1x B200 (the driver's BENCH_rNN.json is the graded number)\n\n" % tag)
+        f.write("* headline: **%.1f pairs/s** device-resident (%.2f ms/step), e2e %.1f pairs/s (%.2f ms/step, %d B H2D + %d B D2H per step); "
+                "clocks %s\n" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["h2d_bytes_per_step"],
+                                 d["e2e"]["d2h_bytes_per_step"], json.dumps(d.get("clocks"))))
+        for k in ("cfg3", "cfg4", "gpu_reference", "cpu_baseline"):
+            v = d.get(k)
+            if isinstance(v, dict):
+                f.write("* %s: `%s`\n" % (k, json.dumps({a: b for a, b in v.items() if a not in ("workload", "how")})[:900]))
+        r = d.get("roofline")
+        if isinstance(r, dict) and "all_kernels" in r:
+            f.write("\n## roofline (graph-replayed C-ABI calls, HBM-cold rotation over >= 1 GiB; peak %.1f GB/s measured)\n\n" % r["peak"])
+            f.write("dominant: `%s` %s: %.1f us, %.0f GB/s = **%.2f**; hot path = %.2f %% of the step\n\n" % (
+                r["kernel"], json.dumps(r["shape"]), r["ms_per_launch"] * 1e3, r["achieved"], r["frac"], 100 * r["hot_path_share_of_step"]))
+            f.write("| kernel | row | calls/step | ms/step cold | ms/step warm | algorithmic GB/s | frac |\n|---|---|---:|---:|---:|---:|---:|\n")
+            for k, v in sorted(r["all_kernels"].items(), key=lambda kv: -kv[1]["ms_per_step"]):
+                f.write("| %s | %s | %.0f | %.3f | %.3f | %.0f | %.2f |\n" % (k, v["row"], v["calls_per_step"], v["ms_per_step"],
+                                                                           v["ms_per_step_warm"], v["achieved_GB_per_s"], v["frac"]))
+            f.write("\n| launch | shape | cold us | warm us | bytes | overhead bytes | frac |\n|---|---|---:|---:|---:|---:|---:|\n")
+            for l in r["launches"]:
+                f.write("| %s | `%s` | %.1f | %.1f | %d | %d | %.2f |\n" % (l["kernel"], json.dumps(l["shape"]), l["cold_ms"] * 1e3,
+                                                                         l["warm_ms"] * 1e3, l["bytes_per_launch"], l["overhead_bytes"], l["frac"]))
+        s_ = d.get("sweep")
+        if isinstance(s_, dict) and "rows" in s_:
+            f.write("\n## configs[4] sweep (clocks during the sweep: %s)\n\n%s\n\n" % (json.dumps(s_["clocks"]), s_["workload"]))
+            f.write("summary (min / max fraction of the measured peak): `%s`\n\n" % json.dumps(s_["summary"]))
+            f.write("| op | C | H=W | B | dtype | layout | sigma | ms | GB/s | frac | ATen fp32 NCDHW ms | speed-up |\n|---|---:|---:|---:|---|---|---:|---:|---:|---:|---:|---:|\n")
+            for x in s_["rows"]:
+                if "ms" in x:
+                    f.write("| %s | %d | %d | %d | %s | %s | %.1f | %.3f | %.0f | %.2f | %.3f | %.1fx |\n" % (
+                        x["op"], x["C"], x["H"], x["B"], x["dtype"], x["layout"], x["sigma"], x["ms"], x["GB_per_s"], x["frac"],
+                        x["aten_f32_ncdhw_ms"], x["speedup_vs_aten"]))
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
     kernels(tag)
     sweep(tag)
+    bench_blocks(tag)
     print(sorted(os.listdir(PROF)))

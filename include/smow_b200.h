@@ -14,8 +14,10 @@
  *   - return 0 on success, a negative SMOW_E* code for an argument error and a
  *     positive value = cudaError_t for a launch failure.  A human-readable
  *     message for the last failure of the calling thread: smow_last_error();
- *   - no mutable global state except the launch counter and the tuning knobs,
- *     so calls are re-entrant from the forward thread and the autograd thread.
+ *   - no mutable global state except the launch counter, the tuning knobs and the monotonically increasing far-tap
+ *     epoch of the warp backward (its stamp is stored in the CALLER's workspace: do not share one workspace block
+ *     between launches that may be in flight on different streams), so calls are re-entrant from the forward
+ *     thread and the autograd thread.
  *
  * Tensor vocabulary (the reference's own):
  *   frames   T1, T2   the two acquisition dates; a "pair" is one (T1,T2) sample
