@@ -39,10 +39,12 @@ for name, meta in CASES:
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()            # with `ncu --profile-from-start off` only this second launch is captured
     e0.record()
     fn()
     e1.record()
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     print("%-16s %s: %.1f us, %.0f GB/s algorithmic" % (name, {k: v for k, v in meta.items() if k in ("B", "C", "T", "Cd", "Cs", "dtype")},
                                                         ms * 1e3, nbytes / ms / 1e6), flush=True)

@@ -82,8 +82,12 @@ def launches(tag):
 
 
 def ncu_raw(rep):
-    r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
-    rows = list(csv.reader(io.StringIO(r.stdout)))
+    """rows of an ncu report: either a .ncu-rep (converted here) or the raw-page CSV already written on the GPU box."""
+    if rep.endswith(".csv"):
+        text = open(rep).read()
+    else:
+        text = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(text)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     out = []
@@ -118,6 +122,8 @@ def kernels(tag):
                             ("instep", "inside one bench step (SMOW_Net_LW, batch 16; operands partly L2-resident)")):
             rep = os.path.join(OUT, "%s_%s_kernels.ncu-rep" % (tag, part))
             if not os.path.exists(rep):
+                rep = rep[:-len(".ncu-rep")] + ".csv"
+            if not os.path.exists(rep) or os.path.getsize(rep) == 0:
                 continue
             rows = ncu_raw(rep)
             f.write("\n## %s\n\n| # | kernel | %s |\n|---|---|%s\n" % (title, " | ".join(t for _, t in METRICS), "---:|" * len(METRICS)))

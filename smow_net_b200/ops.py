@@ -223,6 +223,7 @@ class _WarpStack(torch.autograd.Function):
         if tuple(flow.shape) != (B, 2, 2, H, W):
             raise RuntimeError("flow_warp: flow must be (B,2,2,H,W)=%s, got %s" % ((B, 2, 2, H, W), tuple(flow.shape)))
         x, layout = _layout5(x, C, ndhwc_ok=_ndhwc_warp_ok(x, C))
+        ctx.flow_dtype = flow.dtype
         flow = flow.float().contiguous()
         out = _empty((B, C, 4, H, W), x, layout)
         xs, ys = base_grid(W, x.device), base_grid(H, x.device)
@@ -252,7 +253,7 @@ class _WarpStack(torch.autograd.Function):
                   gout.data_ptr(), x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),
                   gx.data_ptr(), gflow.data_ptr(), B, C, H, W, _dtype_code(x), ctx.layout,
                   ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
-        return gx, gflow
+        return gx, gflow.to(ctx.flow_dtype)          # the kernels' flow gradient is fp32; a bf16 flow gets it rounded
 
 
 class _WarpPair(torch.autograd.Function):
@@ -266,6 +267,7 @@ class _WarpPair(torch.autograd.Function):
             raise RuntimeError("warp_pair: flow must be (B,2,2,H,W)")
         x1, layout = _layout5(x1, C, ndhwc_ok=_ndhwc_warp_ok(x1, C))
         x2 = _as_layout(x2, layout)
+        ctx.flow_dtype = flow.dtype
         flow = flow.float().contiguous()
         out = _empty((B, C, 4, H, W), x1, layout)
         xs, ys = base_grid(W, x1.device), base_grid(H, x1.device)
@@ -296,7 +298,7 @@ class _WarpPair(torch.autograd.Function):
                   gout.data_ptr(), x1.data_ptr(), x2.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),
                   g1.data_ptr(), g2.data_ptr(), gflow.data_ptr(), B, C, H, W, _dtype_code(x1), ctx.layout,
                   ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
-        return g1, g2, gflow
+        return g1, g2, gflow.to(ctx.flow_dtype)
 
 
 def flow_warp(input, flow, size=None):

@@ -246,3 +246,27 @@ def test_frame_mix_tc_writes_into_a_channel_slice():
     want = torch_ref.ref_cyclic_frame_mix(x, pack[0].t(), pack[1:].transpose(1, 2))
     assert float((buf[:, :C] - want).abs().max()) <= 4e-3 * float(want.abs().max())
     assert bool((buf[:, C:] == 7.0).all())
+
+
+def test_module_runs_in_bf16_storage_on_the_ndhwc_kernels():
+    """north_star's bf16 bar at module level: SMOW_Net_LW with bf16 parameters / activations runs the hot path on the
+    NDHWC bf16 kernels (warp + stack forward / backward, lerp + concat with the fused activation) — no bounce through NCDHW —
+    and its change probabilities stay within 5e-2 of the fp32 module's (bf16 convolutions dominate that difference; the
+    per-operator 2e-2 bound is tests/test_ops_gpu.py's)."""
+    from smow_net_b200 import _lib
+    torch.backends.cudnn.allow_tf32 = True
+    model = helpers.seeded_model("lw", device=DEV).eval()
+    x1, x2 = (t.to(DEV) for t in helpers.seeded_pair(2, seed=9))
+    with torch.no_grad():
+        want = model(x1, x2)
+    half = helpers.seeded_model("lw", device=DEV).bfloat16().train()
+    before = _lib.launch_count()
+    out = half(x1.bfloat16(), x2.bfloat16())
+    out.float().mean().backward()
+    assert _lib.launch_count() - before >= 12          # warp fwd + bwd (+ far pass), five fused lerp + concat levels each way
+    assert out.dtype == torch.bfloat16 and bool(torch.isfinite(out.float()).all())
+    assert all(p.grad is None or bool(torch.isfinite(p.grad.float()).all()) for p in half.parameters())
+    half.eval()
+    with torch.no_grad():
+        got = half(x1.bfloat16(), x2.bfloat16()).float()
+    assert float((got - want).abs().max()) <= 5e-2
