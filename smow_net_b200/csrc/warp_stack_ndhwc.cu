@@ -400,7 +400,7 @@ constexpr int ct_log2(int v) { return v <= 1 ? 0 : 1 + ct_log2(v >> 1); }
 // CT / WT: channel count and row width as compile-time constants (0 = runtime): global addresses are then one base
 // register plus immediates and the item index arithmetic is shifts by constants.
 template <int CT, int WT>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 warp_bwd_ndhwc_tile_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
                            int64_t sB, const float* __restrict__ flow, const float* __restrict__ xs,
                            const float* __restrict__ ys, float* __restrict__ gx1, float* __restrict__ gx2,
@@ -1050,7 +1050,8 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
     if (!gather && (bv < 0 || bv == 4) && shuffle) {
       int R = option(OPT_NDHWC_BWD_ROWS);
       const int lshift = qs < 3 ? qs : 3;
-      if (R <= 0) R = lshift == 3 ? 8 : 12;
+      // measured on B200 (benchmarks/bwd_probe.py, 4 CTAs per SM): 4-row tiles for >= 32 channels, 8-row tiles below
+      if (R <= 0) R = lshift == 3 ? 4 : 8;
       if (R > H) R = H;
       const size_t smem = tile_smem_bytes(R, 1 << lshift);
       if (smem <= 72 * 1024 && (int64_t)HW * C < (1ll << 31)) {
