@@ -215,7 +215,9 @@ def roofline_block(calls, step_ms, device, n_steps_recorded):
                    "§8(d) formulas (frame mix: T-frame tensor read + written once; weight gradients: x and gy read once; "
                    "lerp+concat launches with shape.act = 1 also carry the decoder block's LeakyReLU pass, reference "
                    "models/SMOW_Net.py:137: + 8*Cd*hw*s forward (z read, activated half written — it replaces BOTH the "
-                   "reference's activation kernel and the copy of the decoder half), + 12*Cd*hw*s backward); "
+                   "reference's activation kernel and the copy of the decoder half), + 12*Cd*hw*s backward; with shape.act = 2 "
+                   "they carry the block's BatchNorm too, :136: + 8*Cd*hw*s forward (y read, normalised + activated half written), "
+                   "+ 20*Cd*hw*s backward (reduction pass + apply pass)); "
                    "time = median of CUDA-graph replays of the C-ABI call on fresh operands rotating over >= 1 GiB "
                    "(HBM-cold, no launch gaps), events on the replay stream; overhead_bytes = non-algorithmic traffic of the "
                    "same launch (e.g. the copy of the decoder half); warm = one operand set (L2-resident when it fits)",

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SMOW_ABI_VERSION 7
+#define SMOW_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define SMOW_API __attribute__((visibility("default")))
@@ -157,6 +157,29 @@ SMOW_API int smow_act_tlerp_cat_fwd(const void* z, const void* skip_t1, const vo
                        int B, int Cd, int Cs, int64_t hw, int64_t skip_pair_stride, float slope, int dtype, void* stream);
 SMOW_API int smow_act_tlerp_cat_bwd(const void* gcat, const void* z, void* gz, void* gskip_t1, void* gskip_t2,
                        int B, int Cd, int Cs, int64_t hw, int64_t skip_pair_stride, float slope, int dtype, void* stream);
+
+/* ---- BatchNorm of the decoder blocks, folded into the kernels around it ---------------------------------------------------
+ * conv_trans_block_3d.forward / conv_block_2_3d.forward end with  self.batch(mix) -> self.leaky  (models/SMOW_Net.py:135-137,
+ * models/SMOW_Net_LW.py:133-135,173-175).  In training mode:
+ *   1. smow_frame_mix_apply_tc_stats: the frame mix (above) + per-CTA partial sums (sum y, sum y^2 per channel) from its
+ *      epilogue: stats [smow_frame_mix_stats_parts(B,C,T,hw)][2][C];
+ *   2. smow_bn_finalize: bn[0] = scale = gamma*invstd, bn[1] = shift = beta - mean*scale, bn[2] = mean, bn[3] = invstd
+ *      (bn is a [6][C] fp32 block); running_mean / running_var updated like nn.BatchNorm3d (momentum, unbiased variance);
+ *   3. smow_bn_act_tlerp_cat_fwd: cat[:, :Cd] = leaky_relu(y*scale + shift), cat[:, Cd:] = lerped skip (Cs may be 0);
+ *   backward: smow_bn_act_bwd_reduce (sum du, sum du*xhat -> bn[4], bn[5], dgamma, dbeta) then
+ *   smow_bn_act_tlerp_cat_bwd (gy = scale*(du - k1 - xhat*k2) dense + the lerp's gskip).  fp32, NDHWC, deterministic. */
+SMOW_API int     smow_frame_mix_stats_parts(int B, int C, int T, int64_t hw);
+SMOW_API int     smow_frame_mix_apply_tc_stats(const float* in, const float* wpack, const float* bias, float* out, float* stats,
+                         int B, int C, int T, int64_t hw, int64_t out_pitch, int shift, int own_off, void* stream);
+SMOW_API int     smow_bn_finalize(const float* parts, int nparts, int C, int64_t count, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float momentum, float eps, float* bn, void* stream);
+SMOW_API int     smow_bn_act_tlerp_cat_fwd(const float* y, const float* bn, const float* skip_t1, const float* skip_t2,
+                         float* cat, int B, int Cd, int Cs, int64_t hw, int64_t skip_pair_stride, float slope, void* stream);
+SMOW_API int64_t smow_bn_act_bwd_workspace_bytes(int B, int Cd, int64_t hw);
+SMOW_API int     smow_bn_act_bwd_reduce(const float* gcat, const float* y, float* bn, float* dgamma, float* dbeta,
+                         int B, int Cd, int Cs, int64_t hw, float slope, void* workspace, int64_t workspace_bytes, void* stream);
+SMOW_API int     smow_bn_act_tlerp_cat_bwd(const float* gcat, const float* y, const float* bn, float* gy, float* gskip_t1,
+                         float* gskip_t2, int B, int Cd, int Cs, int64_t hw, int64_t skip_pair_stride, float slope, void* stream);
 
 /* ---- N2: semantic tokenizer (the sole consumer of the warped stack) ---------------------------
  * Replaces, per frame k of the stack, models/SMOW_Net.py:176-187 (= models/SMOW_Net_LW.py:195-206):

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmow_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 F32, BF16 = 0, 1
 NCDHW, NDHWC = 0, 1
 
@@ -33,6 +33,13 @@ SIGNATURES = {
     "smow_tlerp_pair_cat_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _vp]),
     "smow_act_tlerp_cat_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, ctypes.c_float, _i, _vp]),
     "smow_act_tlerp_cat_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, ctypes.c_float, _i, _vp]),
+    "smow_frame_mix_stats_parts": (_i, [_i, _i, _i, _i64]),
+    "smow_frame_mix_apply_tc_stats": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i64, _i64, _i, _i, _vp]),
+    "smow_bn_finalize": (_i, [_fp, _i, _i, _i64, _fp, _fp, _fp, _fp, ctypes.c_float, ctypes.c_float, _fp, _vp]),
+    "smow_bn_act_tlerp_cat_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i64, _i64, ctypes.c_float, _vp]),
+    "smow_bn_act_bwd_workspace_bytes": (_i64, [_i, _i, _i64]),
+    "smow_bn_act_bwd_reduce": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i64, ctypes.c_float, _vp, _i64, _vp]),
+    "smow_bn_act_tlerp_cat_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i64, _i64, ctypes.c_float, _vp]),
     "smow_tokenizer_workspace_bytes": (_i64, [_i, _i, _i64]),
     "smow_tokenizer_fwd": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i64, _i, _i, _vp, _i64, _vp]),
     "smow_tokenizer_bwd": (_i, [_fp, _vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i64, _i, _i, _vp, _i64, _vp]),

@@ -78,6 +78,8 @@ struct MixTcParams {
   int tmem_cols;     // power of two >= max(32, Nc)
   int out_cw;        // channels per output staging tile: 32 (128-byte swizzle) or 16 (64-byte swizzle)
   const float* bias; // [T][C] or null
+  float* stats;      // persistent kernel only: per-CTA BatchNorm partial sums [cta][2][C] (sum y, sum y^2), or null
+  int hw;            // pixels per frame (row mask of ragged tiles for the statistics)
 };
 
 __global__ void __launch_bounds__(128)
@@ -275,6 +277,7 @@ mix_apply_tcp_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
     // ---- epilogue warps: TMEM lane quadrant = warp % 4
     const int q = warp & 3, row = q * 32 + lane;
     const bool leader = threadIdx.x == 64;
+    float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};           // BatchNorm partial sums of this thread's (row group, column)
     int i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
       const int f = t % p.T, rest = t / p.T, tile = rest % p.ntiles, b = rest / p.ntiles, acc = i & 1;
@@ -307,6 +310,34 @@ mix_apply_tcp_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       }
       tc_fence_before_sync();
       mbar_arrive(&tempty_bar[acc]);                                        // accumulator free for the MMA warp
+      if (p.stats != nullptr) {
+        // BatchNorm statistics of the block (reference models/SMOW_Net.py:136): column sums of the staged tile, read back
+        // conflict-free through the swizzle; rows past the frame's last pixel (ragged tile) are masked out
+        epi_bar_sync();
+        const int et = threadIdx.x - 64, valid = p.hw - tile * TC_M < TC_M ? p.hw - tile * TC_M : TC_M;
+        if (p.out_cw == 32) {
+          const int c = et & 31, rg = et >> 5;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            if (k >= p.Nc / 32) break;
+            const uint8_t* tb = sb + (size_t)k * TC_A_BYTES + (c & 3) * 4;
+            float a = 0.f, b2 = 0.f;
+            for (int r = rg * 32; r < rg * 32 + 32; ++r) {
+              const float v = r < valid ? *reinterpret_cast<const float*>(tb + r * 128 + ((((c >> 2) ^ (r & 7))) << 4)) : 0.f;
+              a += v; b2 = fmaf(v, v, b2);
+            }
+            ssum[k] += a; ssq[k] += b2;
+          }
+        } else {
+          const int c = et & 15, rg = et >> 4;
+          float a = 0.f, b2 = 0.f;
+          for (int r = rg * 16; r < rg * 16 + 16; ++r) {
+            const float v = r < valid ? *reinterpret_cast<const float*>(sb + r * 64 + ((((c >> 2) ^ ((r >> 1) & 3))) << 4) + (c & 3) * 4) : 0.f;
+            a += v; b2 = fmaf(v, v, b2);
+          }
+          ssum[0] += a; ssq[0] += b2;
+        }
+      }
       fence_proxy_async();
       epi_bar_sync();
       if (leader) {
@@ -319,6 +350,28 @@ mix_apply_tcp_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       }
     }
     if (leader) bulk_wait_read0();
+    if (p.stats != nullptr) {
+      // row groups -> one (sum, sum of squares) per channel and CTA, added in a fixed order
+      epi_bar_sync();
+      float* sc = reinterpret_cast<float*>(stg);                           // [groups][2][Nc]
+      const int et = threadIdx.x - 64;
+      const int groups = p.out_cw == 32 ? 4 : 8, cw = p.out_cw, c = et % cw, rg = et / cw;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (k >= (p.out_cw == 32 ? p.Nc / 32 : 1)) break;
+        sc[(rg * 2 + 0) * p.Nc + k * 32 + c] = ssum[k];
+        sc[(rg * 2 + 1) * p.Nc + k * 32 + c] = ssq[k];
+      }
+      epi_bar_sync();
+      for (int e = et; e < 2 * p.Nc; e += 128) {
+        const int which = e / p.Nc, cc = e - which * p.Nc;
+        if (cc < p.C) {
+          float t = 0.f;
+          for (int g2 = 0; g2 < groups; ++g2) t += sc[(g2 * 2 + which) * p.Nc + cc];
+          p.stats[((size_t)blockIdx.x * 2 + which) * p.C + cc] = t;
+        }
+      }
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -359,8 +412,41 @@ int smow_frame_mix_tc_supported(int C, int T) {
   return (tc_plan(C, p, nsplit) && (T == 2 || T == 4)) ? 1 : 0;
 }
 
+static int frame_mix_apply_tc_impl(const float* in, const float* wpack, const float* bias, float* out, int B, int C, int T,
+                                   int64_t hw, int64_t out_pitch, int shift, int own_off, float* stats, int* stats_ctas,
+                                   void* stream);
+
 int smow_frame_mix_apply_tc(const float* in, const float* wpack, const float* bias, float* out, int B, int C, int T,
                             int64_t hw, int64_t out_pitch, int shift, int own_off, void* stream) {
+  return frame_mix_apply_tc_impl(in, wpack, bias, out, B, C, T, hw, out_pitch, shift, own_off, nullptr, nullptr, stream);
+}
+
+// number of per-CTA partial rows smow_frame_mix_apply_tc_stats writes (0: this shape has no statistics epilogue)
+int smow_frame_mix_stats_parts(int B, int C, int T, int64_t hw) {
+  MixTcParams p;
+  int nsplit = 1;
+  if (B <= 0 || hw <= 0 || (T != 2 && T != 4) || !tc_plan(C, p, nsplit) || p.kc > 2 || nsplit != 1) return 0;
+  const int w_bytes = ((1 + T) * p.kc * p.Nc * 128 + 1023) & ~1023;
+  const int out_b = p.out_cw == 32 ? (p.Nc / 32) * TC_A_BYTES : TC_M * 64;
+  const int fixed = w_bytes + 2 * out_b + 1024;
+  const int per_sm = (110 * 1024 - fixed) / TC_A_BYTES >= 3 ? 2 : 1;
+  const int64_t total = (int64_t)B * T * ((hw + TC_M - 1) / TC_M);
+  const int64_t nctas = (int64_t)device_info().sms * per_sm;
+  return (int)(nctas < total ? nctas : total);
+}
+
+int smow_frame_mix_apply_tc_stats(const float* in, const float* wpack, const float* bias, float* out, float* stats, int B,
+                                  int C, int T, int64_t hw, int64_t out_pitch, int shift, int own_off, void* stream) {
+  if (!stats || !aligned16(stats)) return fail(SMOW_EINVAL, "frame_mix_tc: statistics buffer missing / misaligned");
+  int ctas = 0;
+  const int rc = frame_mix_apply_tc_impl(in, wpack, bias, out, B, C, T, hw, out_pitch, shift, own_off, stats, &ctas, stream);
+  if (rc == 0 && ctas != smow_frame_mix_stats_parts(B, C, T, hw)) return fail(SMOW_EINVAL, "frame_mix_tc: statistics plan mismatch");
+  return rc;
+}
+
+static int frame_mix_apply_tc_impl(const float* in, const float* wpack, const float* bias, float* out, int B, int C, int T,
+                                   int64_t hw, int64_t out_pitch, int shift, int own_off, float* stats, int* stats_ctas,
+                                   void* stream) {
   if (!in || !wpack || !out || B <= 0 || hw <= 0) return fail(SMOW_EINVAL, "frame_mix_tc: bad shape / null pointer");
   if (!smow_frame_mix_tc_supported(C, T)) return fail(SMOW_EDTYPE, "frame_mix_tc: unsupported C = %d / T = %d", C, T);
   if (out_pitch < C || out_pitch % 4 != 0) return fail(SMOW_EINVAL, "frame_mix_tc: out_pitch must be >= C and a multiple of 4");
@@ -372,6 +458,8 @@ int smow_frame_mix_apply_tc(const float* in, const float* wpack, const float* bi
   if (!tc_plan(C, p, nsplit)) return fail(SMOW_EDTYPE, "frame_mix_tc: unsupported C = %d", C);
   p.C = C; p.T = T; p.ntiles = (int)ntiles; p.shift = ((shift % T) + T) % T; p.own_off = ((own_off % T) + T) % T;
   p.bias = bias;
+  p.stats = nullptr;
+  p.hw = (int)hw;
   const int stage_bytes = TC_A_BYTES + p.b_bytes;
   size_t smem = (size_t)p.stages * stage_bytes;
   const size_t out_bytes = p.out_cw == 32 ? (size_t)(p.Nc / 32) * TC_A_BYTES : (size_t)TC_M * 64;
@@ -412,6 +500,7 @@ int smow_frame_mix_apply_tc(const float* in, const float* wpack, const float* bi
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(SMOW_EDTYPE, "frame_mix_tc: shared memory plan failed for C = %d", C);
     MixTcParams pp = p;
+    pp.stats = stats;
     pp.stages = stages;
     pp.tmem_cols = 32;
     while (pp.tmem_cols < 2 * p.Nc) pp.tmem_cols *= 2;
@@ -422,9 +511,11 @@ int smow_frame_mix_apply_tc(const float* in, const float* wpack, const float* bi
     int64_t nctas = (int64_t)device_info().sms * per_sm;
     if (nctas > total_tiles) nctas = total_tiles;
     mix_apply_tcp_kernel<<<(unsigned)nctas, TCP_THREADS, psmem, (cudaStream_t)stream>>>(tm_in, tm_w, tm_out, pp, (int)total_tiles);
+    if (stats_ctas) *stats_ctas = (int)nctas;
     count_launch();
     return check_launch("frame_mix_apply_tc");
   }
+  if (stats) return fail(SMOW_EDTYPE, "frame_mix_tc: the statistics epilogue exists for C <= 64 only (got C = %d)", C);
   const dim3 grid((unsigned)total_tiles, (unsigned)nsplit);
   mix_apply_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(tm_in, tm_w, tm_out, p);
   count_launch();

@@ -168,6 +168,17 @@ tlerp_cat_bwd_kernel(const T* __restrict__ gcat, T* __restrict__ g1, T* __restri
 // bytes of cat (the dec part, then the lerped skip part of the same pixel), so every 32-byte sector is completed
 // by one warp even when Cd*sizeof(T) is not a multiple of 32 (SMOW_Net_LW's 28+16 channel level).  The skip
 // vectors are re-read once per slot (4x, from L2/L1 — they are a small fraction of the concat).
+// BatchNorm-apply (per-channel scale | shift, fp32 tensors only) + LeakyReLU of the decoder half
+template <typename T>
+__device__ __forceinline__ Vec<T> affine_leaky_vec(Vec<T> v, const float* __restrict__ affine, int Cd, int c0, float slope) {
+#pragma unroll
+  for (int j = 0; j < Vec<T>::N; ++j) {
+    const float f = fmaf(cvtf<T>(v.v[j]), __ldg(affine + c0 + j), __ldg(affine + Cd + c0 + j));
+    v.v[j] = fromf<T>(f > 0.f ? f : f * slope);
+  }
+  return v;
+}
+
 // LeakyReLU of the decoder half, fused into its copy (slope == 1: a plain bit-exact copy)
 template <typename T>
 __device__ __forceinline__ Vec<T> leaky_vec(Vec<T> v, float slope) {
@@ -185,7 +196,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, const T* __restrict__ s2,
                            int64_t sB, T* __restrict__ cat, int Cd, int Cs, int64_t hw, int64_t n_items,
-                           bool do_copy, bool do_lerp, FastDiv fqt, FastDiv fhw, float slope) {
+                           bool do_copy, bool do_lerp, FastDiv fqt, FastDiv fhw, float slope,
+                           const float* __restrict__ affine) {
   constexpr int V = Vec<T>::N;
   const int Ct = Cd + Cs;
   const int64_t qd = Cd / V, qt = Ct / V;
@@ -198,7 +210,10 @@ tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, 
       fast_split(i, fqt, r, vt);               // r = (b*4 + slot)*hw + p
       T* dst = cat + ((int64_t)i * V);         // = cat + r*Ct + vt*V: the output is written densely
       if (vt < uqd) {
-        if (do_copy) stv(dst, leaky_vec(ldv_stream(dec + ((int64_t)r * Cd + vt * V)), slope));
+        if (do_copy) {
+          const Vec<T> v = ldv_stream(dec + ((int64_t)r * Cd + vt * V));
+          stv(dst, affine ? affine_leaky_vec(v, affine, Cd, (int)(vt * V), slope) : leaky_vec(v, slope));
+        }
         continue;
       }
       if (!do_lerp) continue;
@@ -223,7 +238,10 @@ tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, 
     int64_t r, vt;
     split_index(i, qt, small, r, vt);          // r = (b*4 + slot)*hw + p
     if (vt < qd) {
-      if (do_copy) stv(cat + r * Ct + vt * V, leaky_vec(ldv_stream(dec + r * Cd + vt * V), slope));
+      if (do_copy) {
+        const Vec<T> v = ldv_stream(dec + r * Cd + vt * V);
+        stv(cat + r * Ct + vt * V, affine ? affine_leaky_vec(v, affine, Cd, (int)(vt * V), slope) : leaky_vec(v, slope));
+      }
       continue;
     }
     if (!do_lerp) continue;
@@ -285,7 +303,11 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 act_tlerp_cat_bwd_ndhwc_kernel(const T* __restrict__ gcat, const T* __restrict__ z, T* __restrict__ gz, T* __restrict__ g1,
                                T* __restrict__ g2, int64_t sB, int Cd, int Cs, int64_t hw, int64_t n_dec, int64_t n_skip,
-                               int nb_dec, FastDiv fqd, FastDiv fqs, FastDiv fhw, float slope) {
+                               int nb_dec, FastDiv fqd, FastDiv fqs, FastDiv fhw, float slope,
+                               const float* __restrict__ bn) {
+  // bn (fp32 tensors only, or null): [6][Cd] = scale | shift | mean | invstd | k1 = sum(du)/N | k2 = sum(du * xhat)/N.  With it
+  // `z` is the block's PRE-BatchNorm tensor y and the dec branch is the whole BatchNorm + LeakyReLU backward:
+  //   u = y*scale + shift, du = g * (u > 0 ? 1 : slope), xhat = (y - mean) * invstd, dy = scale * (du - k1 - xhat * k2)
   constexpr int V = Vec<T>::N;
   const int Ct = Cd + Cs;
   if ((int)blockIdx.x < nb_dec) {
@@ -297,15 +319,29 @@ act_tlerp_cat_bwd_ndhwc_kernel(const T* __restrict__ gcat, const T* __restrict__
       else split_index(i, qd, false, r, v);
       const Vec<T> g = ldv_stream(gcat + r * Ct + v * V), zz = ldv_stream(z + i * V);
       Vec<T> o;
+      if (bn != nullptr) {
+        const int c0 = (int)(v * V);
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const float gg = cvtf<T>(g.v[j]);
-        o.v[j] = fromf<T>(cvtf<T>(zz.v[j]) > 0.f ? gg : gg * slope);
+        for (int j = 0; j < V; ++j) {
+          const int c = c0 + j;
+          const float y = cvtf<T>(zz.v[j]), sc = __ldg(bn + c);
+          const float u = fmaf(y, sc, __ldg(bn + Cd + c));
+          const float gg = cvtf<T>(g.v[j]), du = u > 0.f ? gg : gg * slope;
+          const float xh = (y - __ldg(bn + 2 * Cd + c)) * __ldg(bn + 3 * Cd + c);
+          o.v[j] = fromf<T>(sc * (du - __ldg(bn + 4 * Cd + c) - xh * __ldg(bn + 5 * Cd + c)));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float gg = cvtf<T>(g.v[j]);
+          o.v[j] = fromf<T>(cvtf<T>(zz.v[j]) > 0.f ? gg : gg * slope);
+        }
       }
       stv(gz + i * V, o);
     }
     return;
   }
+  if (n_skip == 0) return;
   const LerpW lw = lerp_weights();
   const int64_t qs = Cs / V, fs = hw * Ct;
   const int nb = gridDim.x - nb_dec;
@@ -379,7 +415,7 @@ static int bwd_impl(const T* gcat, T* g1, T* g2, int64_t sB, int64_t sC, int B, 
 
 template <typename T>
 static int fwd_ndhwc(const T* dec, const T* s1, const T* s2, int64_t sB, T* cat, int B, int Cd, int Cs, int64_t hw,
-                     cudaStream_t st, float slope = 1.f) {
+                     cudaStream_t st, float slope = 1.f, const float* affine = nullptr) {
   constexpr int V = Vec<T>::N;
   const bool do_lerp = s1 != nullptr, do_copy = dec != nullptr && Cd > 0;
   if (!do_lerp && !do_copy) return 0;
@@ -390,24 +426,25 @@ static int fwd_ndhwc(const T* dec, const T* s1, const T* s2, int64_t sB, T* cat,
   const int cap = device_info().sms * 8;
   const int nb = (int)((n_items + 255) / 256 < cap ? (n_items + 255) / 256 : cap);
   tlerp_cat_fwd_ndhwc_kernel<T><<<nb, 256, 0, st>>>(dec, s1, s2, sB, cat, Cd, Cs, hw, n_items, do_copy, do_lerp,
-                                                    make_fastdiv((Cd + Cs) / V), make_fastdiv(hw), slope);
+                                                    make_fastdiv((Cd + Cs) / V), make_fastdiv(hw), slope, affine);
   count_launch();
   return check_launch("tlerp_cat_fwd (NDHWC)");
 }
 
 template <typename T>
 static int act_bwd_ndhwc(const T* gcat, const T* z, T* gz, T* g1, T* g2, int64_t sB, int B, int Cd, int Cs, int64_t hw,
-                         float slope, cudaStream_t st) {
+                         float slope, cudaStream_t st, const float* bn = nullptr) {
   constexpr int V = Vec<T>::N;
-  if (Cd <= 0 || Cd % V || Cs % V || !aligned16(gcat) || !aligned16(z) || !aligned16(gz) || !aligned16(g1) || !aligned16(g2) || sB % V)
+  if (Cd <= 0 || Cd % V || Cs % V || !aligned16(gcat) || !aligned16(z) || !aligned16(gz) ||
+      (Cs > 0 && (!aligned16(g1) || !aligned16(g2) || sB % V)))
     return fail(SMOW_EALIGN, "act_tlerp_cat NDHWC needs Cd > 0, Cd and Cs multiples of %d and 16 B aligned tensors", V);
   const int64_t n_dec = (int64_t)B * 4 * hw * (Cd / V), n_skip = (int64_t)B * hw * (Cs / V);
   const int cap = device_info().sms * 8;
   const int nb_dec = (int)((n_dec + 255) / 256 < cap ? (n_dec + 255) / 256 : cap);
   const int nb_skip = (int)((n_skip + 255) / 256 < cap ? (n_skip + 255) / 256 : cap);
   act_tlerp_cat_bwd_ndhwc_kernel<T><<<nb_dec + nb_skip, 256, 0, st>>>(gcat, z, gz, g1, g2, sB, Cd, Cs, hw, n_dec, n_skip, nb_dec,
-                                                                       make_fastdiv(Cd / V), make_fastdiv(Cs / V),
-                                                                       make_fastdiv(hw), slope);
+                                                                       make_fastdiv(Cd / V), make_fastdiv(Cs > 0 ? Cs / V : 1),
+                                                                       make_fastdiv(hw), slope, bn);
   count_launch();
   return check_launch("act_tlerp_cat_bwd (NDHWC)");
 }
@@ -503,6 +540,26 @@ int smow_act_tlerp_cat_bwd(const void* gcat, const void* z, void* gz, void* gski
                                 skip_pair_stride, B, Cd, Cs, hw, slope, st);
   return act_bwd_ndhwc<__nv_bfloat16>((const __nv_bfloat16*)gcat, (const __nv_bfloat16*)z, (__nv_bfloat16*)gz,
                                       (__nv_bfloat16*)gskip_t1, (__nv_bfloat16*)gskip_t2, skip_pair_stride, B, Cd, Cs, hw, slope, st);
+}
+
+// BatchNorm-apply + LeakyReLU + lerp + concat (fp32, NDHWC).  bn: [>= 2][Cd] = scale | shift (smow_bn_finalize).  Cs may be 0
+// (no skip: the output is the activated block output itself, skip pointers NULL).
+int smow_bn_act_tlerp_cat_fwd(const float* y, const float* bn, const float* skip_t1, const float* skip_t2, float* cat, int B,
+                              int Cd, int Cs, int64_t hw, int64_t skip_pair_stride, float slope, void* stream) {
+  if (!y || !bn || !cat || B <= 0 || Cd <= 0 || Cs < 0 || hw <= 0) return fail(SMOW_EINVAL, "bn_act_tlerp_cat: bad argument");
+  if ((Cs > 0) != (skip_t1 != nullptr) || (skip_t1 == nullptr) != (skip_t2 == nullptr))
+    return fail(SMOW_EINVAL, "bn_act_tlerp_cat: skip pointers must match Cs");
+  if (!aligned16(bn)) return fail(SMOW_EALIGN, "bn_act_tlerp_cat: 16 B alignment");
+  return fwd_ndhwc<float>(y, skip_t1, skip_t2, skip_pair_stride, cat, B, Cd, Cs, hw, (cudaStream_t)stream, slope, bn);
+}
+
+// second half of the backward (after smow_bn_act_bwd_reduce filled bn[4], bn[5]): gy dense + the lerp's gskip, one launch
+int smow_bn_act_tlerp_cat_bwd(const float* gcat, const float* y, const float* bn, float* gy, float* gskip_t1, float* gskip_t2,
+                              int B, int Cd, int Cs, int64_t hw, int64_t skip_pair_stride, float slope, void* stream) {
+  if (!gcat || !y || !bn || !gy || B <= 0 || Cd <= 0 || Cs < 0 || hw <= 0) return fail(SMOW_EINVAL, "bn_act_tlerp_cat: bad argument");
+  if (Cs > 0 && (!gskip_t1 || !gskip_t2)) return fail(SMOW_EINVAL, "bn_act_tlerp_cat: gskip pointers missing");
+  if (!aligned16(bn)) return fail(SMOW_EALIGN, "bn_act_tlerp_cat: 16 B alignment");
+  return act_bwd_ndhwc<float>(gcat, y, gy, gskip_t1, gskip_t2, skip_pair_stride, B, Cd, Cs, hw, slope, (cudaStream_t)stream, bn);
 }
 
 int smow_tlerp_pair_cat_bwd(const void* gcat, void* gskip_t1, void* gskip_t2, int B, int Cd, int Cs, int64_t hw,

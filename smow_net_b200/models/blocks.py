@@ -129,6 +129,31 @@ def tensor_core_mix_enabled():
     return bool(torch.backends.cudnn.allow_tf32)
 
 
+def fused_bn_enabled(frames5d, shared, own, bn, cs=0):
+    """The fully fused decoder block tail — frame mix with BatchNorm statistics from its epilogue, then BatchNorm-apply +
+    LeakyReLU (+ temporal lerp + concat) in one pass — needs: training-mode batch statistics, the tensor-core mix
+    (cudnn.allow_tf32), C <= 64 (the persistent kernel) and 16-byte channel vectors.  Tests switch it off to route the block
+    through the oracle seams."""
+    if not (bn.training and bn.track_running_stats and bn.affine and bn.momentum is not None and len(own) == 4):
+        return False
+    if not (frames5d.is_cuda and frames5d.dtype == torch.float32 and frames5d.dim() == 5 and frames5d.shape[2] == 4):
+        return False
+    from .. import ops
+    c_out = shared.weight.shape[1] if isinstance(shared, nn.ConvTranspose3d) else shared.weight.shape[0]
+    return tensor_core_mix_enabled() and cs % 4 == 0 and ops.frame_mix_tc_stats_supported(frames5d, c_out, 4)
+
+
+def mix_bn_act(frames5d, shared, own, bn, slope, skip=None, skip_pair=None):
+    """leaky_relu(bn(cyclic_frame_mix(frames))) [concatenated with the temporally up-sampled skip] on the fused kernels."""
+    from .. import ops
+    bias = None
+    if shared.bias is not None:
+        bias = torch.stack([shared.bias + own[(f + 1) % 4].bias for f in range(4)])
+    pack = torch.stack([m.weight[:, :, 0, 0, 0] for m in [shared] + list(own)])
+    y, parts = ops.frame_mix_tc_stats(frames5d, pack, bias, 4, 1, 1, nk=not isinstance(shared, nn.ConvTranspose3d))
+    return ops.bn_act_tlerp_cat(y, parts, bn, slope, skip=skip, skip_pair=skip_pair)
+
+
 def cyclic_frame_mix(frames5d, shared, own, shift=1, own_off=1):
     """out[:, :, f] = shared(frames[f]) + own[(f + own_off) % T](frames[(f + shift) % T]),  T = len(own).
 
@@ -209,7 +234,12 @@ class TemporalDeconvMix(nn.Module):
         the decoder half.  `skip` (B,Cs,2,h,w) or `skip_pair` = two (B,Cs,h,w) frames."""
         from .. import ops
         cs = skip.shape[1] if skip is not None else skip_pair[0].shape[1]
-        z = self.pre_activation(x)
+        own = [getattr(self, "conv3d_time_%d" % i) for i in range(1, 5)]
+        s = self.conv3d_spatial(x)
+        if fused_bn_enabled(s, self.conv3d_time_5, own, self.batch, cs):
+            # frame mix (+ BatchNorm statistics) -> BatchNorm-apply + LeakyReLU + lerp + concat: two passes over the block output
+            return mix_bn_act(s, self.conv3d_time_5, own, self.batch, self.leaky.negative_slope, skip=skip, skip_pair=skip_pair)
+        z = self.batch(cyclic_frame_mix(s, self.conv3d_time_5, own))
         if ops.act_cat_supported(z, cs):
             slope = self.leaky.negative_slope
             return ops.act_tlerp_cat(z, skip, slope) if skip is not None else ops.act_tlerp_pair_cat(z, *skip_pair, slope)
@@ -249,8 +279,10 @@ class SpatialConvMix(nn.Module):
 
     def forward(self, x):
         own = [getattr(self, "conv3d_t%d" % i) for i in range(1, 5)]
-        y = cyclic_frame_mix(self.conv3d_s(x), self.conv3d_t5, own)
-        return self.l(self.b(y))
+        s = self.conv3d_s(x)
+        if fused_bn_enabled(s, self.conv3d_t5, own, self.b):
+            return mix_bn_act(s, self.conv3d_t5, own, self.b, self.l.negative_slope)
+        return self.l(self.b(cyclic_frame_mix(s, self.conv3d_t5, own)))
 
 
 class PointwiseConvBN(nn.Module):

@@ -680,7 +680,7 @@ class _FrameMixTC(torch.autograd.Function):
     (`nk=False`: ConvTranspose3d weights as stored); its gradient comes back in the same orientation."""
 
     @staticmethod
-    def forward(ctx, x, pack, bias, T, shift, own_off, nk):
+    def forward(ctx, x, pack, bias, T, shift, own_off, nk, want_stats=False):
         B, C, _, H, W = x.shape
         x = x.contiguous(memory_format=torch.channels_last_3d)
         pack = pack.contiguous()
@@ -688,17 +688,24 @@ class _FrameMixTC(torch.autograd.Function):
         y = torch.empty_like(x, memory_format=torch.channels_last_3d)
         b = None if bias is None else bias.contiguous().float()
         lib = _lib.load()
+        ctx.save_for_backward(x, pack)
+        ctx.cfg = (T, shift, own_off, nk, bias is not None)
         with torch.cuda.device_of(x):
             _meta(B=B, C=C, T=T, hw=H * W, tc=1)
+            if want_stats:      # BatchNorm partial sums (sum y, sum y^2 per channel and CTA) from the kernel's epilogue
+                parts = torch.empty((int(lib.smow_frame_mix_stats_parts(B, C, T, H * W)), 2, C), dtype=torch.float32, device=x.device)
+                _call("frame_mix_fwd", frame_mix_apply_bytes(B, C, T, H * W), lib.smow_frame_mix_apply_tc_stats,
+                      x.data_ptr(), w_nk.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(), parts.data_ptr(),
+                      B, C, T, H * W, C, shift, own_off, _stream())
+                ctx.mark_non_differentiable(parts)
+                return y, parts
             _call("frame_mix_fwd", frame_mix_apply_bytes(B, C, T, H * W), lib.smow_frame_mix_apply_tc,
                   x.data_ptr(), w_nk.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(), B, C, T, H * W, C,
                   shift, own_off, _stream())
-        ctx.save_for_backward(x, pack)
-        ctx.cfg = (T, shift, own_off, nk, bias is not None)
         return y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, *_unused):
         x, pack = ctx.saved_tensors
         T, shift, own_off, nk, has_bias = ctx.cfg
         B, C, _, H, W = x.shape
@@ -726,7 +733,7 @@ class _FrameMixTC(torch.autograd.Function):
                       x.data_ptr(), gy.data_ptr(), gpack.data_ptr(), B, C, T, H * W, shift, own_off,
                       ws.data_ptr(), n, _stream())
         gbias = gy.sum(dim=(0, 3, 4)).t() if has_bias else None             # (T, C)
-        return gx, gpack, gbias, None, None, None, None
+        return gx, gpack, gbias, None, None, None, None, None
 
 
 def frame_mix_tc(x, pack, bias=None, T=4, shift=1, own_off=1, nk=True):
@@ -742,7 +749,117 @@ def frame_mix_tc(x, pack, bias=None, T=4, shift=1, own_off=1, nk=True):
         raise RuntimeError("frame_mix_tc: pack must be fp32 (1+T,C,C)=%s, got %s %s" % ((1 + T, C, C), pack.dtype, tuple(pack.shape)))
     if bias is not None and (tuple(bias.shape) != (T, C) or bias.dtype != torch.float32):
         raise RuntimeError("frame_mix_tc: bias must be fp32 (T,C)")
-    return _FrameMixTC.apply(x, pack, bias, T, shift, own_off, nk)
+    return _FrameMixTC.apply(x, pack, bias, T, shift, own_off, nk, False)
+
+
+def frame_mix_tc_stats_supported(x, c_out, T):
+    """The statistics epilogue lives in the persistent kernel (C <= 64)."""
+    return frame_mix_tc_supported(x, c_out, T) and int(_lib.load().smow_frame_mix_stats_parts(
+        int(x.shape[0]), int(c_out), int(T), int(x.shape[3] * x.shape[4]))) > 0
+
+
+def frame_mix_tc_stats(x, pack, bias=None, T=4, shift=1, own_off=1, nk=True):
+    """frame_mix_tc that also returns the BatchNorm partial sums of its output: (y, parts[(ctas, 2, C)])."""
+    _require_cuda(x, pack, bias)
+    C = x.shape[1] if x.dim() == 5 else -1
+    if not frame_mix_tc_stats_supported(x, C, T) or tuple(pack.shape) != (1 + T, C, C) or pack.dtype != torch.float32:
+        raise RuntimeError("frame_mix_tc_stats: needs an fp32 CUDA (B,C,%d,H,W) stack with C <= 64 and a (1+T,C,C) pack" % T)
+    return _FrameMixTC.apply(x, pack, bias, T, shift, own_off, nk, True)
+
+
+# ----------------------------------------------------------------------------- BatchNorm + LeakyReLU + lerp + concat
+def bn_act_fwd_bytes(B, Cd, hw):
+    """y read once, the activated decoder half written once."""
+    return B * 8 * Cd * hw * 4
+
+
+def bn_act_bwd_bytes(B, Cd, hw):
+    """reduction pass: gradient slice + y read; apply pass: both read again, d y written."""
+    return B * 20 * Cd * hw * 4
+
+
+class _BnActTLerpCat(torch.autograd.Function):
+    """cat([leaky_relu(batch_norm(y)), tlerp(T1, T2)], 1) with training-mode batch statistics taken from `parts` (the
+    frame-mix epilogue's partial sums): one tiny finalize launch + ONE pass forward; reduce + finalize + ONE pass backward."""
+
+    @staticmethod
+    def forward(ctx, y, parts, gamma, beta, running_mean, running_var, momentum, eps, a, b, slope, stacked):
+        B, Cd, _, h, w = y.shape
+        Cs = 0 if a is None else a.shape[1]
+        hw = h * w
+        y = y.contiguous(memory_format=torch.channels_last_3d)
+        bn = torch.empty((6, Cd), dtype=torch.float32, device=y.device)
+        cat = torch.empty((B, Cd + Cs, 4, h, w), dtype=torch.float32, device=y.device, memory_format=torch.channels_last_3d)
+        pair_stride = (2 if stacked else 1) * Cs * hw
+        lib = _lib.load()
+        with torch.cuda.device_of(y):
+            _lib.check(lib.smow_bn_finalize(parts.data_ptr(), parts.shape[0], Cd, B * 4 * hw, gamma.data_ptr(), beta.data_ptr(),
+                                            None if running_mean is None else running_mean.data_ptr(),
+                                            None if running_var is None else running_var.data_ptr(), float(momentum), float(eps),
+                                            bn.data_ptr(), _stream()), "bn_finalize")
+            _meta(B=B, Cd=Cd, Cs=Cs, hw=hw, dtype=_lib.F32, layout=_lib.NDHWC, pair=0, act=2)
+            _call("tlerp_cat_fwd", tlerp_fwd_bytes(B, Cd, Cs, hw, 4) + bn_act_fwd_bytes(B, Cd, hw), lib.smow_bn_act_tlerp_cat_fwd,
+                  y.data_ptr(), bn.data_ptr(), None if a is None else a.data_ptr(), None if b is None else b.data_ptr(),
+                  cat.data_ptr(), B, Cd, Cs, hw, pair_stride, float(slope), _stream())
+        ctx.save_for_backward(y, bn)
+        ctx.cfg = (B, Cd, Cs, h, w, float(slope), stacked)
+        return cat
+
+    @staticmethod
+    def backward(ctx, gcat):
+        y, bn = ctx.saved_tensors
+        B, Cd, Cs, h, w, slope, stacked = ctx.cfg
+        hw = h * w
+        gcat = gcat.contiguous(memory_format=torch.channels_last_3d)
+        bn = bn.clone()                                              # rows 4, 5 are written by the reduction
+        gy = torch.empty_like(y, memory_format=torch.channels_last_3d)
+        dgamma, dbeta = torch.empty(Cd, device=y.device), torch.empty(Cd, device=y.device)
+        ga = gb = None
+        if Cs:
+            if stacked:
+                gs = torch.empty((B, Cs, 2, h, w), dtype=torch.float32, device=y.device, memory_format=torch.channels_last_3d)
+                ga, gb = gs[:, :, 0], gs[:, :, 1]
+            else:
+                ga = torch.empty((B, Cs, h, w), dtype=torch.float32, device=y.device, memory_format=torch.channels_last)
+                gb = torch.empty_like(ga, memory_format=torch.channels_last)
+        pair_stride = (2 if stacked else 1) * Cs * hw
+        lib = _lib.load()
+        n = int(lib.smow_bn_act_bwd_workspace_bytes(B, Cd, hw))
+        ws = torch.empty(max(n, 16), dtype=torch.uint8, device=y.device)
+        with torch.cuda.device_of(y):
+            _meta(B=B, Cd=Cd, Cs=Cs, hw=hw, dtype=_lib.F32, layout=_lib.NDHWC, pair=0, act=2)
+            _call("tlerp_cat_bwd", tlerp_bwd_bytes(B, Cs, hw, 4) + bn_act_bwd_bytes(B, Cd, hw), lib.smow_bn_act_bwd_reduce,
+                  gcat.data_ptr(), y.data_ptr(), bn.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), B, Cd, Cs, hw, slope,
+                  ws.data_ptr(), n, _stream())
+            _lib.check(lib.smow_bn_act_tlerp_cat_bwd(gcat.data_ptr(), y.data_ptr(), bn.data_ptr(), gy.data_ptr(),
+                                                     None if ga is None else ga.data_ptr(), None if gb is None else gb.data_ptr(),
+                                                     B, Cd, Cs, hw, pair_stride, slope, _stream()), "bn_act_tlerp_cat_bwd")
+        return gy, None, dgamma, dbeta, None, None, None, None, ga, gb, None, None
+
+
+def bn_act_tlerp_cat(y, parts, bn_module, slope, skip=None, skip_pair=None):
+    """Training-mode ``cat([leaky_relu(bn_module(y)), interpolate(skip, (4,h,w))], 1)`` (or just the activated block output when
+    no skip is given) with the batch statistics taken from `parts` — the partial sums the tcgen05 frame-mix epilogue produced
+    (``frame_mix_tc_stats``).  Updates ``running_mean`` / ``running_var`` / ``num_batches_tracked`` like nn.BatchNorm3d
+    (reference models/SMOW_Net.py:136-137 + :64-94)."""
+    _require_cuda(y, parts, bn_module.weight, skip, *(skip_pair or ()))
+    if y.dtype != torch.float32 or y.dim() != 5 or y.shape[2] != 4 or y.shape[1] % 4:
+        raise RuntimeError("bn_act_tlerp_cat: y must be an fp32 (B,Cd,4,h,w) CUDA tensor with Cd % 4 == 0")
+    a = b = None
+    stacked = False
+    if skip is not None:
+        skip = skip.contiguous(memory_format=torch.channels_last_3d)
+        a, b, stacked = skip[:, :, 0], skip[:, :, 1], True
+    elif skip_pair is not None:
+        a = skip_pair[0].contiguous(memory_format=torch.channels_last)
+        b = skip_pair[1].contiguous(memory_format=torch.channels_last)
+    if a is not None and (a.dtype != torch.float32 or a.shape[1] % 4 or tuple(a.shape[-2:]) != tuple(y.shape[-2:])):
+        raise RuntimeError("bn_act_tlerp_cat: skip frames must be fp32 (B,Cs,h,w) with Cs % 4 == 0 matching y")
+    cat = _BnActTLerpCat.apply(y, parts, bn_module.weight, bn_module.bias, bn_module.running_mean, bn_module.running_var,
+                               bn_module.momentum, bn_module.eps, a, b, slope, stacked)
+    if bn_module.num_batches_tracked is not None:
+        bn_module.num_batches_tracked.add_(1)
+    return cat
 
 
 # ----------------------------------------------------------------------------- N1: the OFW flow head

@@ -57,8 +57,37 @@ def build(name, m, dev, gen, sigma=0.3):
     if name in ("tlerp_cat_fwd", "tlerp_cat_bwd"):
         B, Cd, Cs, hw, dt, lay = m["B"], m["Cd"], m["Cs"], m["hw"], _dt(m["dtype"]), m["layout"]
         s = 4 if dt == torch.float32 else 2
-        skip = _t((B, Cs, 2, hw, 1), dev, dt, lay, gen)
+        skip = _t((B, max(Cs, 4), 2, hw, 1), dev, dt, lay, gen) if Cs else None
+        if Cs == 0 and m.get("act") != 2:
+            raise KeyError("tlerp without a skip")
+        skip = skip if Cs else torch.zeros(1, device=dev)
         cat = _t((B, Cd + Cs, 4, hw, 1), dev, dt, lay, gen)
+        if m.get("act") == 2:  # BatchNorm-apply + LeakyReLU folded in (ops.bn_act_tlerp_cat): y -> cat[:, :Cd]
+            z = _t((B, Cd, 4, hw, 1), dev, torch.float32, lay, gen)
+            bn = torch.rand(6, Cd, device=dev, generator=gen) + 0.5
+            s1 = skip if Cs else None
+            s2 = skip[:, :, 1] if Cs else None
+            if name == "tlerp_cat_fwd":
+                fn = lambda: _lib.check(lib.smow_bn_act_tlerp_cat_fwd(z.data_ptr(), bn.data_ptr(), s1.data_ptr() if Cs else None,  # noqa: E731
+                                                                      s2.data_ptr() if Cs else None, cat.data_ptr(), B, Cd, Cs, hw,
+                                                                      2 * Cs * hw, 0.2, st()), name)
+                alg = ops.tlerp_fwd_bytes(B, Cd, Cs, hw, 4) + ops.bn_act_fwd_bytes(B, Cd, hw)
+                return fn, alg, alg, (z, skip, cat, bn)
+            gy = torch.empty_like(z)
+            gskip = torch.empty_like(skip) if Cs else None
+            g2 = gskip[:, :, 1] if Cs else None
+            dg, db = torch.empty(Cd, device=dev), torch.empty(Cd, device=dev)
+            n = int(lib.smow_bn_act_bwd_workspace_bytes(B, Cd, hw))
+            ws = torch.empty(max(n, 16), dtype=torch.uint8, device=dev)
+
+            def fn():
+                _lib.check(lib.smow_bn_act_bwd_reduce(cat.data_ptr(), z.data_ptr(), bn.data_ptr(), dg.data_ptr(), db.data_ptr(), B, Cd, Cs,
+                                                      hw, 0.2, ws.data_ptr(), n, st()), name)
+                _lib.check(lib.smow_bn_act_tlerp_cat_bwd(cat.data_ptr(), z.data_ptr(), bn.data_ptr(), gy.data_ptr(),
+                                                         gskip.data_ptr() if Cs else None, g2.data_ptr() if Cs else None, B, Cd, Cs, hw,
+                                                         2 * Cs * hw, 0.2, st()), name)
+            alg = ops.tlerp_bwd_bytes(B, Cs, hw, 4) + ops.bn_act_bwd_bytes(B, Cd, hw)
+            return fn, alg, alg, (z, cat, gy, gskip, bn, ws)
         if m.get("act"):       # LeakyReLU of the decoder block folded in: z -> cat[:, :Cd], no copy (ops.act_tlerp_*)
             z = _t((B, Cd, 4, hw, 1), dev, dt, lay, gen)
             s2 = skip[:, :, 1]

@@ -82,6 +82,7 @@ def use_oracle_ops(monkeypatch):
         return torch_ref.ref_cyclic_frame_mix(frames5d, blocks._mix_matrix(shared),
                                               torch.stack([blocks._mix_matrix(m) for m in own]), bias, shift, own_off)
     monkeypatch.setattr(blocks, "cyclic_frame_mix", mix)
+    monkeypatch.setattr(blocks, "fused_bn_enabled", lambda *a, **k: False)     # BatchNorm stays the framework's in the oracle arm
 
 
 def import_reference():

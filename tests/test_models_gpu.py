@@ -270,3 +270,114 @@ def test_module_runs_in_bf16_storage_on_the_ndhwc_kernels():
     with torch.no_grad():
         got = half(x1.bfloat16(), x2.bfloat16()).float()
     assert float((got - want).abs().max()) <= 5e-2
+
+
+# ------------------------------------------------------------------------------------------------ fused BatchNorm tail of the decoder blocks
+@pytest.mark.parametrize("case", [(2, 28, 16, 40, 36, "stack"), (3, 32, 24, 16, 16, "pair"), (2, 16, 0, 64, 64, None), (1, 64, 32, 9, 7, "pair")])
+def test_bn_act_tlerp_cat_matches_batch_norm_leaky_interpolate_cat(case):
+    """ops.bn_act_tlerp_cat in isolation, strict fp32: given y and its per-channel partial sums, the result equals the reference
+    tail  torch.cat([leaky_relu(BatchNorm3d(y)), interpolate(skip, (4,h,w))], 1)  (models/SMOW_Net.py:136-137 + :64-94) in
+    training mode — output, d y, d gamma, d beta, d skip, and the running statistics — within 1e-5 of each tensor's scale."""
+    import torch.nn.functional as F
+    from oracle import torch_ref
+    from smow_net_b200 import ops
+    B, Cd, Cs, h, w, kind = case
+    g = torch.Generator().manual_seed(Cd * 7 + Cs)
+    y = (torch.randn(B, Cd, 4, h, w, generator=g) * 1.7 + 0.4).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    skip = torch.randn(B, max(Cs, 1), 2, h, w, generator=g).to(DEV).contiguous(memory_format=torch.channels_last_3d) if Cs else None
+    gcat = torch.randn(B, Cd + Cs, 4, h, w, generator=g).to(DEV)
+    bn_a, bn_b = torch.nn.BatchNorm3d(Cd).to(DEV).train(), torch.nn.BatchNorm3d(Cd).to(DEV).train()
+    with torch.no_grad():
+        bn_a.weight.copy_(torch.rand(Cd, generator=g) + 0.5)
+        bn_a.bias.copy_(torch.randn(Cd, generator=g) * 0.3)
+        bn_a.running_mean.copy_(torch.randn(Cd, generator=g) * 0.1)
+    bn_b.load_state_dict(bn_a.state_dict())
+    # mine
+    yi = y.clone(memory_format=torch.preserve_format).requires_grad_(True)
+    si = skip.clone(memory_format=torch.preserve_format).requires_grad_(True) if Cs else None
+    rows = yi.detach().permute(0, 2, 3, 4, 1).reshape(-1, Cd)
+    parts = torch.stack((rows.double().sum(0), (rows.double() ** 2).sum(0))).float().unsqueeze(0).contiguous()   # ONE partial row
+    kw = {} if not Cs else ({"skip": si} if kind == "stack" else {"skip_pair": (si[:, :, 0], si[:, :, 1])})
+    cat = ops.bn_act_tlerp_cat(yi, parts, bn_a, 0.2, **kw)
+    cat.backward(gcat)
+    # reference tail
+    yr = y.clone(memory_format=torch.preserve_format).requires_grad_(True)
+    sr = skip.clone(memory_format=torch.preserve_format).requires_grad_(True) if Cs else None
+    act = F.leaky_relu(bn_b(yr), 0.2)
+    want = torch_ref.ref_tlerp_cat(act, sr) if Cs else act
+    want.backward(gcat)
+
+    def close(a, b, tol=1e-5):
+        return float((a - b).abs().max()) <= tol * max(1.0, float(b.abs().max()))
+    assert close(cat, want) and close(yi.grad, yr.grad) and close(bn_a.weight.grad, bn_b.weight.grad, 2e-5)
+    assert close(bn_a.bias.grad, bn_b.bias.grad, 2e-5)
+    if Cs:
+        assert close(si.grad, sr.grad)
+    assert close(bn_a.running_mean, bn_b.running_mean) and close(bn_a.running_var, bn_b.running_var)
+    assert int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("case", [("deconv", 28, 16, 20, 24), ("deconv_wide", 32, 32, 16, 16), ("conv", 16, 0, 64, 64), ("deconv", 64, 32, 8, 8)])
+def test_fused_decoder_block_tail_matches_the_unfused_block(case):
+    """A whole decoder block in training mode under PyTorch's default TF32 flags: tcgen05 frame mix with BatchNorm statistics
+    from its epilogue + BatchNorm-apply / LeakyReLU / lerp / concat in one pass, against the SAME block routed through the
+    oracle seams (fp32 frame mix, nn.BatchNorm3d, LeakyReLU, interpolate + cat).  TF32 bound: 5e-3 of each tensor's scale for
+    the output, every parameter gradient, the input gradient and the running statistics; the statistics epilogue itself is
+    checked against sums of the kernel's own output at 1e-5."""
+    import copy
+    from smow_net_b200 import _lib, ops
+    from smow_net_b200.models import blocks
+    kind, C, Cs, h, w = case
+    torch.manual_seed(11)
+    if kind == "conv":
+        blk = blocks.SpatialConvMix(C + 8, C).to(DEV)
+        x = torch.randn(2, C + 8, 4, h, w, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    else:
+        blk = blocks.TemporalDeconvMix(C, C, wide=kind == "deconv_wide").to(DEV)
+        x = torch.randn(2, C, 4, h // 2, w // 2, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+    blocks.convs_channels_last_3d(blk)
+    ref = copy.deepcopy(blk)
+    blk.train(); ref.train()
+    skip = torch.randn(2, Cs, 2, h, w, device=DEV).contiguous(memory_format=torch.channels_last_3d) if Cs else None
+    gout = torch.randn(2, C + Cs, 4, h, w, device=DEV)
+
+    def run(m, fused):
+        torch.backends.cudnn.allow_tf32 = fused            # oracle arm: strict fp32 (the autouse fixture restores the flag)
+        saved = blocks.fused_bn_enabled
+        if not fused:
+            blocks.fused_bn_enabled = lambda *a, **k: False
+        try:
+            xi = x.clone(memory_format=torch.preserve_format).requires_grad_(True)
+            si = skip.clone(memory_format=torch.preserve_format).requires_grad_(True) if Cs else None
+            before = _lib.launch_count()
+            out = m.forward_into_concat(xi, skip=si) if Cs else m(xi)
+            out.backward(gout)
+            n = _lib.launch_count() - before
+        finally:
+            blocks.fused_bn_enabled = saved
+        grads = {k: p.grad.clone() for k, p in m.named_parameters()}
+        stats = {k: b.clone() for k, b in m.named_buffers()}
+        return out.detach(), xi.grad, (si.grad if Cs else None), grads, stats, n
+    mine = run(blk, True)
+    want = run(ref, False)
+    assert mine[5] == 8                                    # mix+stats, finalize, apply | reduce, finalize, apply, mix bwd, wgrad (2)
+    scale = lambda t: max(1.0, float(t.abs().max()))       # noqa: E731
+    assert float((mine[0] - want[0]).abs().max()) <= 5e-3 * scale(want[0])
+    assert float((mine[1] - want[1]).abs().max()) <= 5e-3 * scale(want[1])
+    if Cs:
+        assert float((mine[2] - want[2]).abs().max()) <= 1e-5 * scale(want[2])
+    for k in want[3]:
+        assert float((mine[3][k] - want[3][k]).abs().max()) <= 5e-3 * scale(want[3][k]), k
+    for k in want[4]:
+        assert float((mine[4][k].float() - want[4][k].float()).abs().max()) <= 5e-3 * scale(want[4][k].float()), k
+    # the statistics epilogue against the kernel's own output
+    torch.backends.cudnn.allow_tf32 = True
+    pack = torch.randn(5, C, C, device=DEV) / C ** 0.5
+    z = torch.randn(2, C, 4, h, w, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    y, parts = ops.frame_mix_tc_stats(z, pack, None, 4, 1, 1, nk=True)
+    rows = y.permute(0, 2, 3, 4, 1).reshape(-1, C).double()
+    assert float((parts[:, 0].double().sum(0) - rows.sum(0)).abs().max()) <= 1e-5 * max(1.0, float(rows.sum(0).abs().max()))
+    assert float((parts[:, 1].double().sum(0) - (rows ** 2).sum(0)).abs().max()) <= 1e-5 * float((rows ** 2).sum(0).max())
