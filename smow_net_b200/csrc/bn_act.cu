@@ -14,17 +14,24 @@
 namespace smow {
 
 // bn: [6][C] = scale | shift | mean | invstd | k1 | k2 (k1, k2 are written by the backward)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 bn_finalize_kernel(const float* __restrict__ parts, int nparts, int C, double count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
                    float momentum, float eps, float* __restrict__ bn) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
+  // one warp per channel: lanes stride over the partial rows (independent loads in flight), fixed shuffle tree
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < nparts; ++k) {
+  for (int k = lane; k < nparts; k += 32) {
     s1 += (double)parts[((size_t)k * 2 + 0) * C + c];
     s2 += (double)parts[((size_t)k * 2 + 1) * C + c];
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if (lane != 0) return;
   const double mean = s1 / count;
   double var = s2 / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -53,18 +60,32 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ gcat, const float* __restrict
   if (rl < rpi) {
     const float4 sc = __ldg(reinterpret_cast<const float4*>(bn) + v), sh = __ldg(reinterpret_cast<const float4*>(bn + Cd) + v);
     const float4 mu = __ldg(reinterpret_cast<const float4*>(bn + 2 * Cd) + v), is = __ldg(reinterpret_cast<const float4*>(bn + 3 * Cd) + v);
-    for (int64_t r = (int64_t)blockIdx.x * rpi + rl; r < rows; r += (int64_t)gridDim.x * rpi) {
+    const int64_t step = (int64_t)gridDim.x * rpi;
+    int64_t r = (int64_t)blockIdx.x * rpi + rl;
+#define SMOW_BN_ACC(gv, yv, f)                                                   \
+  {                                                                              \
+    const float u = fmaf(yv.f, sc.f, sh.f), du = u > 0.f ? gv.f : gv.f * slope;  \
+    a1.f += du;                                                                  \
+    a2.f = fmaf(du, (yv.f - mu.f) * is.f, a2.f);                                 \
+  }
+#define SMOW_BN_ROW(gv, yv) SMOW_BN_ACC(gv, yv, x) SMOW_BN_ACC(gv, yv, y) SMOW_BN_ACC(gv, yv, z) SMOW_BN_ACC(gv, yv, w)
+    for (; r + 3 * step < rows; r += 4 * step) {                    // four rows in flight per thread
+      float4 g[4], yy[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g[k] = __ldg(reinterpret_cast<const float4*>(gcat + (r + k * step) * Ct) + v);
+        yy[k] = __ldg(reinterpret_cast<const float4*>(y + (r + k * step) * Cd) + v);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { SMOW_BN_ROW(g[k], yy[k]) }
+    }
+    for (; r < rows; r += step) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gcat + r * Ct) + v);
       const float4 yy = __ldg(reinterpret_cast<const float4*>(y + r * Cd) + v);
-#define SMOW_BN_ACC(f)                                                        \
-  {                                                                           \
-    const float u = fmaf(yy.f, sc.f, sh.f), du = u > 0.f ? g.f : g.f * slope; \
-    a1.f += du;                                                               \
-    a2.f = fmaf(du, (yy.f - mu.f) * is.f, a2.f);                              \
-  }
-      SMOW_BN_ACC(x) SMOW_BN_ACC(y) SMOW_BN_ACC(z) SMOW_BN_ACC(w)
-#undef SMOW_BN_ACC
+      SMOW_BN_ROW(g, yy)
     }
+#undef SMOW_BN_ROW
+#undef SMOW_BN_ACC
     float* dst = sm + ((size_t)rl * q + v) * 8;
     *reinterpret_cast<float4*>(dst) = a1;
     *reinterpret_cast<float4*>(dst + 4) = a2;
@@ -78,16 +99,22 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ gcat, const float* __restrict
   }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 bn_act_bwd_finalize_kernel(const float* __restrict__ part, int nparts, int C, double count, float* __restrict__ bn,
                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;      // one warp per channel
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < nparts; ++k) {
+  for (int k = lane; k < nparts; k += 32) {
     s1 += (double)part[((size_t)k * 2 + 0) * C + c];
     s2 += (double)part[((size_t)k * 2 + 1) * C + c];
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if (lane != 0) return;
   bn[4 * C + c] = (float)(s1 / count);
   bn[5 * C + c] = (float)(s2 / count);
   if (dbeta) dbeta[c] = (float)s1;
@@ -110,7 +137,7 @@ extern "C" {
 int smow_bn_finalize(const float* parts, int nparts, int C, int64_t count, const float* gamma, const float* beta,
                      float* running_mean, float* running_var, float momentum, float eps, float* bn, void* stream) {
   if (!parts || !bn || nparts <= 0 || C <= 0 || count <= 0) return fail(SMOW_EINVAL, "bn_finalize: bad argument");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(parts, nparts, C, (double)count, gamma, beta,
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(parts, nparts, C, (double)count, gamma, beta,
                                                                         running_mean, running_var, momentum, eps, bn);
   count_launch();
   return check_launch("bn_finalize");
@@ -136,7 +163,7 @@ int smow_bn_act_bwd_reduce(const float* gcat, const float* y, float* bn, float* 
   cudaStream_t st = (cudaStream_t)stream;
   float* part = reinterpret_cast<float*>(ws);
   bn_act_bwd_reduce_kernel<<<nb, 256, smem, st>>>(gcat, y, bn, rows, Cd, Cd + Cs, slope, part);
-  bn_act_bwd_finalize_kernel<<<(Cd + 127) / 128, 128, 0, st>>>(part, nb, Cd, (double)rows, bn, dgamma, dbeta);
+  bn_act_bwd_finalize_kernel<<<(Cd + 7) / 8, 256, 0, st>>>(part, nb, Cd, (double)rows, bn, dgamma, dbeta);
   count_launch(2);
   return check_launch("bn_act_bwd_reduce");
 }

@@ -169,11 +169,23 @@ tlerp_cat_bwd_kernel(const T* __restrict__ gcat, T* __restrict__ g1, T* __restri
 // by one warp even when Cd*sizeof(T) is not a multiple of 32 (SMOW_Net_LW's 28+16 channel level).  The skip
 // vectors are re-read once per slot (4x, from L2/L1 — they are a small fraction of the concat).
 // BatchNorm-apply (per-channel scale | shift, fp32 tensors only) + LeakyReLU of the decoder half
+// per-channel parameter row `row` of a [rows][Cd] fp32 table for the N channels starting at c0 (c0 % 4 == 0): 16-byte loads
+template <int N>
+__device__ __forceinline__ void ld_params(float (&dst)[N], const float* __restrict__ table, int Cd, int row, int c0) {
+#pragma unroll
+  for (int j = 0; j < N; j += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(table + (size_t)row * Cd + c0 + j));
+    dst[j] = t.x; dst[j + 1] = t.y; dst[j + 2] = t.z; dst[j + 3] = t.w;
+  }
+}
 template <typename T>
 __device__ __forceinline__ Vec<T> affine_leaky_vec(Vec<T> v, const float* __restrict__ affine, int Cd, int c0, float slope) {
+  float sc[Vec<T>::N], sh[Vec<T>::N];
+  ld_params<Vec<T>::N>(sc, affine, Cd, 0, c0);
+  ld_params<Vec<T>::N>(sh, affine, Cd, 1, c0);
 #pragma unroll
   for (int j = 0; j < Vec<T>::N; ++j) {
-    const float f = fmaf(cvtf<T>(v.v[j]), __ldg(affine + c0 + j), __ldg(affine + Cd + c0 + j));
+    const float f = fmaf(cvtf<T>(v.v[j]), sc[j], sh[j]);
     v.v[j] = fromf<T>(f > 0.f ? f : f * slope);
   }
   return v;
@@ -321,14 +333,16 @@ act_tlerp_cat_bwd_ndhwc_kernel(const T* __restrict__ gcat, const T* __restrict__
       Vec<T> o;
       if (bn != nullptr) {
         const int c0 = (int)(v * V);
+        float sc[V], sh[V], mu[V], is[V], k1[V], k2[V];
+        ld_params<V>(sc, bn, Cd, 0, c0); ld_params<V>(sh, bn, Cd, 1, c0); ld_params<V>(mu, bn, Cd, 2, c0);
+        ld_params<V>(is, bn, Cd, 3, c0); ld_params<V>(k1, bn, Cd, 4, c0); ld_params<V>(k2, bn, Cd, 5, c0);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          const int c = c0 + j;
-          const float y = cvtf<T>(zz.v[j]), sc = __ldg(bn + c);
-          const float u = fmaf(y, sc, __ldg(bn + Cd + c));
+          const float y = cvtf<T>(zz.v[j]);
+          const float u = fmaf(y, sc[j], sh[j]);
           const float gg = cvtf<T>(g.v[j]), du = u > 0.f ? gg : gg * slope;
-          const float xh = (y - __ldg(bn + 2 * Cd + c)) * __ldg(bn + 3 * Cd + c);
-          o.v[j] = fromf<T>(sc * (du - __ldg(bn + 4 * Cd + c) - xh * __ldg(bn + 5 * Cd + c)));
+          const float xh = (y - mu[j]) * is[j];
+          o.v[j] = fromf<T>(sc[j] * (du - k1[j] - xh * k2[j]));
         }
       } else {
 #pragma unroll
