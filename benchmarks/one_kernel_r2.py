@@ -22,6 +22,8 @@ CASES = [
     ("warp_stack_bwd", {"B": B, "C": 64, "H": H, "W": H, "dtype": BF16, "layout": ND, "pair": 0}),
     ("tlerp_cat_fwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 1}),
     ("tlerp_cat_bwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 1}),
+    ("tlerp_cat_fwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 2}),
+    ("tlerp_cat_bwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 2}),
     ("tokenizer_fwd", {"B": B, "C": C, "hw": H * H}),
     ("tokenizer_bwd", {"B": B, "C": C, "hw": H * H}),
     ("frame_mix_fwd", {"B": B, "C": C, "T": 4, "hw": H * H, "tc": 1}),

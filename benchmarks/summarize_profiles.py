@@ -37,7 +37,7 @@ METRICS = [
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
 ]
-OURS = ("warp_", "tlerp_", "act_tlerp_", "tok_", "mix_", "flow_head_")      # kernel-name prefixes of libsmow_b200.so
+OURS = ("warp_", "tlerp_", "act_tlerp_", "tok_", "mix_", "flow_head_", "bn_")      # kernel-name prefixes of libsmow_b200.so
 TO_BYTES = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 TO_US = {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}
 
@@ -77,7 +77,7 @@ def launches(tag):
             ours += us if mine else 0
             if us / total >= 0.003 or mine:
                 f.write("| %s%s | %d | %.1f | %.2f %% |\n" % ("**" if mine else "", k + ("**" if mine else ""), c, us, 100 * us / total))
-        f.write("\nHand-written kernels (rows A1-A5: warp_*, tlerp_*, act_tlerp_*; N1: flow_head_*; N2: tok_*; N4: mix_*): %.1f us = "
+        f.write("\nHand-written kernels (rows A1-A5: warp_*, tlerp_*, act_tlerp_*; N1: flow_head_*; N2: tok_*; N4: mix_*, bn_*): %.1f us = "
                 "%.2f %% of the step's kernel time.\n" % (ours, 100 * ours / total))
 
 
@@ -153,7 +153,7 @@ def kernels(tag):
     if traffic:
         op_of = {"warp_fwd": "warp_stack_fwd", "warp_stack_fwd": "warp_stack_fwd", "warp_bwd": "warp_stack_bwd",
                  "warp_stack_bwd": "warp_stack_bwd", "tlerp_cat_fwd": "tlerp_cat_fwd", "tlerp_cat_bwd": "tlerp_cat_bwd",
-                 "act_tlerp_cat_bwd": "tlerp_cat_bwd", "tok_fwd": "tokenizer_fwd", "tok_bwd": "tokenizer_bwd",
+                 "act_tlerp_cat_bwd": "tlerp_cat_bwd", "bn_act_bwd": "tlerp_cat_bwd", "tok_fwd": "tokenizer_fwd", "tok_bwd": "tokenizer_bwd",
                  "mix_apply": "frame_mix_apply", "mix_wgrad": "frame_mix_wgrad", "flow_head_fwd": "flow_head_fwd",
                  "flow_head_bwd": "flow_head_bwd"}
         per_op = {}
@@ -162,7 +162,7 @@ def kernels(tag):
                 if k.startswith(pre):
                     o = per_op.setdefault(op, {"launches": 0, "bytes": 0.0, "largest": 0.0})
                     o["largest"] = max(o["largest"], bmax)
-                    if "far" not in k and "combine" not in k:      # side kernels of the same C-ABI call
+                    if "far" not in k and "combine" not in k and not k.startswith("bn_"):      # side kernels of the same C-ABI call
                         o["launches"] += n
                     o["bytes"] += b
                     break
