@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmow_b200.so")
-SOURCES = ["abi.cu", "warp_stack.cu", "warp_stack_bwd_tiled.cu", "warp_stack_cvec.cu", "warp_stack_ndhwc.cu", "tlerp_cat.cu", "tokenizer.cu", "frame_mix.cu", "frame_mix_tc.cu", "flow_head.cu", "bn_act.cu"]
+SOURCES = ["abi.cu", "warp_stack.cu", "warp_stack_bwd_tiled.cu", "warp_stack_cvec.cu", "warp_stack_ndhwc.cu", "tlerp_cat.cu", "tokenizer.cu", "tokenizer_mma.cu", "frame_mix.cu", "frame_mix_tc.cu", "flow_head.cu", "bn_act.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

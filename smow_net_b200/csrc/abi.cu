@@ -23,6 +23,7 @@ static Knob g_knobs[OPT_COUNT] = {
     {"ndhwc_bwd_rows", {0}},     // NDHWC tile gather: rows per tile (0 = auto, about 512 pixels per tile)
     {"ndhwc_bwd_pf", {-1}},      // NDHWC tile gather: L2 prefetch distance in tiles (-1 = auto: 4 per SM, 0 = off)
     {"tc_debug", {0}},           // bring-up switches of the tcgen05 kernels (0 in production)
+    {"tok_variant", {-1}},       // tokenizer: -1 = auto (tensor-core MMA kernels for C = 16 / 32), 0 = FP32-pipe kernels
 };
 
 int fail(int code, const char* fmt, ...) {

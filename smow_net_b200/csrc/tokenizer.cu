@@ -14,18 +14,12 @@
 // two exponentials and accumulates a 2 x CG tile of the token matrix — no cross-lane traffic at all for C <= 16, one
 // G-lane butterfly per logit beyond.  The work is ~300 FP32 instructions per 64-byte pixel: these kernels are bound by
 // FP32 issue, not by HBM.  Everything is summed in a fixed order (no float atomics): results are bit-reproducible.
-#include "common.cuh"
 #include "bulk.cuh"
+#include "tokenizer.cuh"
 
 namespace smow {
 
-constexpr int TOK_L = 8;            // token_len of both reference models
 constexpr int TOK_FWD_THREADS = 256, TOK_BWD_THREADS = 128;
-
-// chunk = pixels per CTA: its C*4-byte rows are one contiguous range of the stack, staged in shared memory by ONE bulk
-// copy (cp.async.bulk + mbarrier) so that the stack leaves HBM exactly once per pass
-struct TokGeom { int C, G, lpshift, chunk; int64_t hw; int nchunks; };      // LP = 4*G = 1 << lpshift lanes per pixel
-__host__ __device__ inline int tok_chunk_px(int C) { return 16384 / C < 512 ? 16384 / C : 512; }   // <= 64 KB of x
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -390,6 +384,7 @@ tok_bwd_combine_kernel(const float* __restrict__ part, float* __restrict__ gwa, 
   }
 }
 
+static bool tok_use_mma(int C) { return option(OPT_TOK_VARIANT) != 0 && tok_mma_supported(C); }
 static int tok_geom(TokGeom& g, int B, int C, int64_t hw, const void* x, int dtype, int layout) {
   if (B <= 0 || C <= 0 || hw <= 0 || !x) return fail(SMOW_EINVAL, "tokenizer: bad shape / null pointer");
   if (dtype != SMOW_F32 || layout != SMOW_NDHWC)
@@ -400,7 +395,7 @@ static int tok_geom(TokGeom& g, int B, int C, int64_t hw, const void* x, int dty
   if ((CG != 4 && CG != 8 && CG != 16) || C % CG || g.lpshift < 0)
     return fail(SMOW_EINVAL, "tokenizer: C must be 4, 8 or 16 * (1, 2, 4, 8) (got C = %d)", C);
   if (!aligned16(x)) return fail(SMOW_EALIGN, "tokenizer: stack not 16 B aligned");
-  g.chunk = tok_chunk_px(C);
+  g.chunk = tok_use_mma(C) ? tok_mma_chunk_px(C) : tok_chunk_px(C);
   g.nchunks = (int)((hw + g.chunk - 1) / g.chunk);
   if ((int64_t)4 * B > 65535) return fail(SMOW_ERANGE, "tokenizer: batch too large for one launch");
   return 0;
@@ -421,7 +416,10 @@ extern "C" {
 
 int64_t smow_tokenizer_workspace_bytes(int B, int C, int64_t hw) {
   if (C <= 0 || hw <= 0 || B <= 0) return 0;
-  const int64_t chunk = tok_chunk_px(C), nchunks = (hw + chunk - 1) / chunk;
+  // sized for the smaller chunk of the two kernel families, so that the knob can change between the query and the call
+  int64_t chunk = tok_chunk_px(C);
+  if (tok_mma_supported(C) && tok_mma_chunk_px(C) < chunk) chunk = tok_mma_chunk_px(C);
+  const int64_t nchunks = (hw + chunk - 1) / chunk;
   return (int64_t)4 * B * nchunks * (2 * TOK_L + TOK_L * C) * (int64_t)sizeof(float);
 }
 
@@ -436,11 +434,14 @@ int smow_tokenizer_fwd(const void* x, const float* wa, const float* ba, float* t
   float* part = reinterpret_cast<float*>(ws);
   const dim3 grid(g.nchunks, 4 * B);
   const size_t smem = tok_smem(g, TOK_FWD_THREADS);
+  // C = 16 / 32 (the two models): the GEMMs run as 3xTF32 tensor-core MMAs (tokenizer_mma.cu) unless tok_variant = 0
+  const bool mma = tok_use_mma(C);
 #define SMOW_TOK_FWD(CG, ITER)                                \
   tok_allow_smem(tok_fwd_chunk_kernel<CG, ITER>, smem);       \
   tok_fwd_chunk_kernel<CG, ITER><<<grid, TOK_FWD_THREADS, smem, st>>>((const float*)x, wa, ba, part, g)
   // pixels per thread = chunk * LP / threads: 8 for C <= 16 (512-pixel chunks, 4 lanes per pixel), 16 beyond
-  switch (C / g.G) {
+  if (mma) tok_fwd_mma_launch((const float*)x, wa, ba, part, g, B, st);
+  else switch (C / g.G) {
     case 4: SMOW_TOK_FWD(4, 8); break;
     case 8: SMOW_TOK_FWD(8, 8); break;
     default: if (g.G == 1) { SMOW_TOK_FWD(16, 8); } else { SMOW_TOK_FWD(16, 16); } break;
@@ -463,10 +464,12 @@ int smow_tokenizer_bwd(const float* gtokens, const void* x, const float* wa, con
   float* part = reinterpret_cast<float*>(ws);
   const dim3 grid(g.nchunks, 4 * B);
   const size_t smem = tok_smem(g, TOK_BWD_THREADS);
+  const bool mma = tok_use_mma(C);
 #define SMOW_TOK_BWD(CG)                                 \
   tok_allow_smem(tok_bwd_chunk_kernel<CG>, smem);        \
   tok_bwd_chunk_kernel<CG><<<grid, TOK_BWD_THREADS, smem, st>>>(gtokens, (const float*)x, wa, ba, tokens, stats, (float*)gx, part, g)
-  switch (C / g.G) {
+  if (mma) tok_bwd_mma_launch(gtokens, (const float*)x, wa, ba, tokens, stats, (float*)gx, part, g, B, st);
+  else switch (C / g.G) {
     case 4: SMOW_TOK_BWD(4); break;
     case 8: SMOW_TOK_BWD(8); break;
     default: SMOW_TOK_BWD(16); break;
