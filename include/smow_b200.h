@@ -193,7 +193,11 @@ SMOW_API int     smow_bn_act_tlerp_cat_bwd(const float* gcat, const float* y, co
  *   workspace: smow_tokenizer_workspace_bytes(B,C,hw) bytes, 16-byte aligned, uninitialised.
  * Backward: gx (B,C,4,H,W) NDHWC = d loss / d x through both the attention and the pooling,
  *   gwa (8,C), gba (8) overwritten (not accumulated); tokens / stats are the forward's outputs.
- * All sums run in a fixed order: results are bit-reproducible.                                  */
+ * All sums run in a fixed order: results are bit-reproducible.
+ * C = 16 / 32 (the two models): the three 8-token-wide GEMMs run on the tensor cores as warp-level TF32 MMAs
+ * with a hi/lo split of both operands (3xTF32, fp32 accumulation): fp32-class accuracy (<= 4e-6 of scale
+ * against a float64 evaluation, tests hold it to the same 1e-5 bar as the FP32-pipe kernels), ~2x their
+ * speed.  Knob "tok_variant" = 0 selects the FP32-pipe kernels (the only family for other C).     */
 SMOW_API int64_t smow_tokenizer_workspace_bytes(int B, int C, int64_t hw);
 SMOW_API int smow_tokenizer_fwd(const void* x, const float* wa, const float* ba,
                        float* tokens, float* stats, int B, int C, int64_t hw,

@@ -28,10 +28,17 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
-// x = hi + lo + O(2^-22 x): hi, lo both exactly representable in TF32
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+// x = hi + lo + O(2^-22 x): hi, lo both exactly representable in TF32.  Round-to-nearest conversions (cvt.rna is emulated
+// with ~4 integer instructions on sm_100a): used for the operands that are split once per CTA.
+__device__ __forceinline__ void split_tf32_rn(float x, uint32_t& hi, uint32_t& lo) {
   hi = to_tf32(x);
   lo = to_tf32(x - __uint_as_float(hi));
+}
+// The per-pixel operands are split with two instructions instead: hi = x with the 13 low mantissa bits cleared, lo = x - hi
+// (exact in fp32); the tensor core ignores the low 13 bits of lo, an error below 2^-21 |x| — still fp32-class accuracy.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
@@ -46,10 +53,10 @@ __device__ __forceinline__ void load_row_frags(uint32_t (&f)[C / 8][4], const fl
 #pragma unroll
   for (int q = 0; q < C / 16; ++q) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(src + g * C + 16 * q + 4 * t));
-    split_tf32(v.x, f[2 * q][0], f[2 * q][1]);
-    split_tf32(v.y, f[2 * q][2], f[2 * q][3]);
-    split_tf32(v.z, f[2 * q + 1][0], f[2 * q + 1][1]);
-    split_tf32(v.w, f[2 * q + 1][2], f[2 * q + 1][3]);
+    split_tf32_rn(v.x, f[2 * q][0], f[2 * q][1]);
+    split_tf32_rn(v.y, f[2 * q][2], f[2 * q][3]);
+    split_tf32_rn(v.z, f[2 * q + 1][0], f[2 * q + 1][1]);
+    split_tf32_rn(v.w, f[2 * q + 1][2], f[2 * q + 1][3]);
   }
 }
 
@@ -210,8 +217,8 @@ tok_bwd_mma_kernel(const float* __restrict__ gtok, const float* __restrict__ x, 
       const int gg = ln >> 2, tt = ln & 3;
       const int ch = 16 * (j >> 1) + 4 * (gg >> 1) + 2 * (j & 1) + (gg & 1);
       uint4 v;
-      split_tf32(__ldg(src + (2 * tt) * C + ch), v.x, v.z);
-      split_tf32(__ldg(src + (2 * tt + 1) * C + ch), v.y, v.w);
+      split_tf32_rn(__ldg(src + (2 * tt) * C + ch), v.x, v.z);
+      split_tf32_rn(__ldg(src + (2 * tt + 1) * C + ch), v.y, v.w);
       vs[(j * 2 + ks) * 32 + ln] = v;
     }
   };
@@ -352,7 +359,7 @@ tok_bwd_mma_kernel(const float* __restrict__ gtok, const float* __restrict__ x, 
 }
 
 bool tok_mma_supported(int C) { return C == 16 || C == 32; }
-int tok_mma_chunk_px(int C) { return C == 16 ? 512 : 256; }       // 32 KB of x per staging buffer
+int tok_mma_chunk_px(int C) { (void)C; return 512; }               // 32 / 64 KB of x per CTA (1024 and 256 measured slower)
 
 template <typename K> static void tokm_allow_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -367,8 +374,8 @@ void tok_fwd_mma_launch(const float* x, const float* wa, const float* ba, float*
     tokm_allow_smem(tok_fwd_mma_kernel<16, 512>, smem);
     tok_fwd_mma_kernel<16, 512><<<grid, TOKM_FWD_THREADS, smem, st>>>(x, wa, ba, part, g);
   } else {
-    tokm_allow_smem(tok_fwd_mma_kernel<32, 256>, smem);
-    tok_fwd_mma_kernel<32, 256><<<grid, TOKM_FWD_THREADS, smem, st>>>(x, wa, ba, part, g);
+    tokm_allow_smem(tok_fwd_mma_kernel<32, 512>, smem);
+    tok_fwd_mma_kernel<32, 512><<<grid, TOKM_FWD_THREADS, smem, st>>>(x, wa, ba, part, g);
   }
 }
 
@@ -381,8 +388,8 @@ void tok_bwd_mma_launch(const float* gtok, const float* x, const float* wa, cons
     tokm_allow_smem(tok_bwd_mma_kernel<16, 512>, smem);
     tok_bwd_mma_kernel<16, 512><<<grid, TOKM_BWD_THREADS, smem, st>>>(gtok, x, wa, ba, tokens, stats, gx, part, g);
   } else {
-    tokm_allow_smem(tok_bwd_mma_kernel<32, 256>, smem);
-    tok_bwd_mma_kernel<32, 256><<<grid, TOKM_BWD_THREADS, smem, st>>>(gtok, x, wa, ba, tokens, stats, gx, part, g);
+    tokm_allow_smem(tok_bwd_mma_kernel<32, 512>, smem);
+    tok_bwd_mma_kernel<32, 512><<<grid, TOKM_BWD_THREADS, smem, st>>>(gtok, x, wa, ba, tokens, stats, gx, part, g);
   }
 }
 
