@@ -217,7 +217,10 @@ tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, 
   const bool small = n_items < (1ll << 31);
   if (small) {          // every index fits 32 bits: multiply-shift divisions, 32-bit offsets (the models' shapes)
     const uint32_t n32 = (uint32_t)n_items, step = gridDim.x * 256u, uqd = (uint32_t)qd;
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n32; i += step) {
+    // The tensor is walked from its END: the producer of `dec` (frame mix / BatchNorm) wrote it front to back, so its tail is
+    // what the L2 still holds; and the consumer of `cat` (a convolution starting at the front) finds our last writes there.
+    for (uint32_t i0 = blockIdx.x * 256u + threadIdx.x; i0 < n32; i0 += step) {
+      const uint32_t i = n32 - 1u - i0;
       uint32_t r, vt;
       fast_split(i, fqt, r, vt);               // r = (b*4 + slot)*hw + p
       T* dst = cat + ((int64_t)i * V);         // = cat + r*Ct + vt*V: the output is written densely
@@ -246,7 +249,8 @@ tlerp_cat_fwd_ndhwc_kernel(const T* __restrict__ dec, const T* __restrict__ s1, 
     }
     return;
   }
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_items; i += (int64_t)gridDim.x * 256) {
+  for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < n_items; i0 += (int64_t)gridDim.x * 256) {
+    const int64_t i = n_items - 1 - i0;
     int64_t r, vt;
     split_index(i, qt, small, r, vt);          // r = (b*4 + slot)*hw + p
     if (vt < qd) {
@@ -325,7 +329,9 @@ act_tlerp_cat_bwd_ndhwc_kernel(const T* __restrict__ gcat, const T* __restrict__
   if ((int)blockIdx.x < nb_dec) {
     const int64_t qd = Cd / V;
     const bool small = n_dec < (1ll << 31);
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_dec; i += (int64_t)nb_dec * 256) {
+    // walked from the END: the reduction pass over the same (gradient slice, y) ran front to back, its tail is L2-resident
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < n_dec; i0 += (int64_t)nb_dec * 256) {
+      const int64_t i = n_dec - 1 - i0;
       int64_t r, v;
       if (small) { uint32_t ur, uv; fast_split((uint32_t)i, fqd, ur, uv); r = ur; v = uv; }
       else split_index(i, qd, false, r, v);
@@ -360,7 +366,8 @@ act_tlerp_cat_bwd_ndhwc_kernel(const T* __restrict__ gcat, const T* __restrict__
   const int64_t qs = Cs / V, fs = hw * Ct;
   const int nb = gridDim.x - nb_dec;
   const bool small = n_skip < (1ll << 31) && (int64_t)4 * hw * Ct < (1ll << 31);
-  for (int64_t i = (int64_t)(blockIdx.x - nb_dec) * 256 + threadIdx.x; i < n_skip; i += (int64_t)nb * 256) {
+  for (int64_t i0 = (int64_t)(blockIdx.x - nb_dec) * 256 + threadIdx.x; i0 < n_skip; i0 += (int64_t)nb * 256) {
+    const int64_t i = n_skip - 1 - i0;
     int64_t bp, vs, b, p;
     if (small) {
       uint32_t ubp, uvs, ub, up;
