@@ -21,7 +21,7 @@ static Knob g_knobs[OPT_COUNT] = {
     {"cvec_prefetch", {3}},      // L2 bulk-prefetch distance of the channel-vectorised kernels, in chunks (0 = off)
     {"bwd_chunk_mb", {0}},       // NDHWC scatter: process the batch in chunks of about this many MB (0 = whole batch)
     {"ndhwc_bwd_rows", {0}},     // NDHWC tile gather: rows per tile (0 = auto, about 512 pixels per tile)
-    {"ndhwc_bwd_pf", {-1}},      // NDHWC tile gather: L2 prefetch distance in tiles (-1 = auto: 4 per SM, 0 = off)
+    {"ndhwc_bwd_pf", {-1}},      // NDHWC tile gather: next item's x taps prefetched into shared-memory slots (-1 = auto: C >= 128, 0 = off, 1 = on)
     {"tc_debug", {0}},           // bring-up switches of the tcgen05 kernels (0 in production)
     {"tok_variant", {-1}},       // tokenizer: -1 = auto (tensor-core MMA kernels for C = 16 / 32), 0 = FP32-pipe kernels
 };

@@ -395,12 +395,17 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gme
 __host__ __device__ inline size_t tile_smem_bytes(int R, int LC) {
   return ((size_t)(R + 2) * TILE_W2 * (LC + 1) + (size_t)R * TILE_W * 3) * 16 + (size_t)R * TILE_W * 8;
 }
+// + the tap slots of the prefetching variant: [2 stages][4 taps][256 threads] x 16 B
+constexpr size_t TILE_SLOT_BYTES = 2 * 4 * 256 * 16;
 constexpr int ct_log2(int v) { return v <= 1 ? 0 : 1 + ct_log2(v >> 1); }
 
 // CT / WT: channel count and row width as compile-time constants (0 = runtime): global addresses are then one base
 // register plus immediates and the item index arithmetic is shifts by constants.
-template <int CT, int WT>
-__global__ void __launch_bounds__(256, 4)
+// PF: the 4 taps of x of the NEXT item are already on their way into per-thread shared-memory slots (cp.async, no registers
+// held while in flight) and its pass-through vector into a register while the current item is computed — the loads of
+// phase 2 were where 1/3 of all stall samples of the non-prefetching kernel sat (ncu source view, profiles/r2_notes.md).
+template <int CT, int WT, bool PF>
+__global__ void __launch_bounds__(256, PF ? 3 : 4)
 warp_bwd_ndhwc_tile_kernel(const float* __restrict__ gout, const float* __restrict__ x1, const float* __restrict__ x2,
                            int64_t sB, const float* __restrict__ flow, const float* __restrict__ xs,
                            const float* __restrict__ ys, float* __restrict__ gx1, float* __restrict__ gx2,
@@ -467,6 +472,42 @@ warp_bwd_ndhwc_tile_kernel(const float* __restrict__ gout, const float* __restri
   // tell the far pass (stream-ordered after this kernel) that it has work; every writer stores the same epoch
   if (found_far) *far_flag = epoch;
   __syncthreads();
+  // set-up of phase 2 (and, PF, the loads of its first item) before phase 1
+  const int n_items = (R * TILE_W) << lshift;
+  const int rowC = W * C;
+  const float* gpass = gout + ((int64_t)(b * 4 + (t ? 3 : 0)) * HW) * C;
+  const float* src = (t ? x2 : x1) + b * sB;
+  float* dst = (t ? gx2 : gx1) + b * sB;
+  const float inv_w = 1.f / (float)W, inv_h = 1.f / (float)H;
+  const int rstride = TILE_W2 * LC;                          // float4 per staged row
+  const int iters = (n_items + 255) >> 8;                    // per chunk
+  // prefetch state (PF only): item (pf_chunk, pf_it) goes to slot stage pf_n & 1
+  float4* slots = reinterpret_cast<float4*>(gacc + R * TILE_W) + threadIdx.x;
+  int pf_chunk = 0, pf_it = 0, pf_n = 0;
+  float4 pass_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&]() {
+    const int it = pf_it * 256 + threadIdx.x;
+    const int pl = it >> lshift, lv = it & (LC - 1);
+    const int hl = pl >> 5, wl = pl & 31;
+    const int h = h0 + hl, w = w0 + wl;
+    if (it < n_items && h < H && w < W) {
+      const float4 own = sc[(hl + 1) * TILE_W2 + wl + 1];
+      const int x0 = (int)own.x, y0 = (int)own.y;            // coordinates are clipped to [0, size-1]: truncation = floor
+      const bool x1ok = x0 + 1 <= W - 1, y1ok = y0 + 1 <= H - 1;
+      const int cb = (pf_chunk << lshift) * 4 + lv * 4;
+      const float* xp = src + ((y0 * W + x0) * C + cb);
+      float4* sl = slots + (pf_n & 1) * 4 * 256;
+      cp_async16_zfill(sl, xp, true);
+      cp_async16_zfill(sl + 256, x1ok ? xp + C : xp, x1ok);
+      cp_async16_zfill(sl + 512, y1ok ? xp + rowC : xp, y1ok);
+      cp_async16_zfill(sl + 768, (x1ok && y1ok) ? xp + rowC + C : xp, x1ok && y1ok);
+      pass_next = __ldg(reinterpret_cast<const float4*>(gpass + (h * W + w) * C + cb));
+    }
+    cp_async_commit();
+    ++pf_n;
+    if (++pf_it == iters) { pf_it = 0; ++pf_chunk; }
+  };
+  if constexpr (PF) prefetch();                              // item 0: in flight during the rest of the prologue
   // ---- phase 1: probe weights, one thread per target pixel ----
   for (int pl = threadIdx.x; pl < R * TILE_W; pl += 256) {
     const int hl = pl >> 5, wl = pl & 31;
@@ -489,44 +530,51 @@ warp_bwd_ndhwc_tile_kernel(const float* __restrict__ gout, const float* __restri
     gacc[pl] = make_float2(0.f, 0.f);
   }
   // ---- phase 2: one thread per (target pixel, channel vector), 32 channels at a time ----
-  const int n_items = (R * TILE_W) << lshift;
-  const int rowC = W * C;
-  const float* gpass = gout + ((int64_t)(b * 4 + (t ? 3 : 0)) * HW) * C;
-  const float* src = (t ? x2 : x1) + b * sB;
-  float* dst = (t ? gx2 : gx1) + b * sB;
-  const float inv_w = 1.f / (float)W, inv_h = 1.f / (float)H;
-  const int rstride = TILE_W2 * LC;                          // float4 per staged row
   for (int chunk = 0; chunk < nchunks; ++chunk) {
     if (chunk > 0) { __syncthreads(); stage(chunk); }
-    cp_async_wait_all();
+    cp_async_wait_all();                                     // the staged tile (and, PF, the slots of this chunk's first item)
     __syncthreads();
     const int cbase = (chunk << lshift) * 4;
-    for (int base = 0; base < n_items; base += 256) {
-      const int it = base + threadIdx.x;
+    for (int itn = 0; itn < iters; ++itn) {
+      const int it = (itn << 8) + threadIdx.x;
       const int pl = it >> lshift, lv = it & (LC - 1);
       const int hl = pl >> 5, wl = pl & 31;
       const int h = h0 + hl, w = w0 + wl;
       const bool live = it < n_items && h < H && w < W;
       float gix = 0.f, giy = 0.f;
       float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 pass = pass_next, xa, xb, xc, xd;
+      if constexpr (PF) {
+        const int q = chunk * iters + itn;
+        const bool has_next = q + 1 < iters * nchunks;       // uniform
+        if (has_next) prefetch();
+        if (itn > 0) {                                       // item q's group is the last but one (or the last)
+          if (has_next) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else cp_async_wait_all();
+        }
+        const float4* sl = slots + (q & 1) * 4 * 256;
+        xa = sl[0]; xb = sl[256]; xc = sl[512]; xd = sl[768];
+      }
       if (live) {
         const float4 wa = wt[pl * 3], wb = wt[pl * 3 + 1];
         const float w8 = wt[pl * 3 + 2].x;
         own = sc[(hl + 1) * TILE_W2 + wl + 1];
         const float x0f = floorf(own.x), y0f = floorf(own.y);
-        const int x0 = (int)x0f, y0 = (int)y0f;
         const float wx0 = __fsub_rn(__fadd_rn(x0f, 1.f), own.x), wx1 = __fsub_rn(own.x, x0f);
         const float wy0 = __fsub_rn(__fadd_rn(y0f, 1.f), own.y), wy1 = __fsub_rn(own.y, y0f);
-        const bool x1ok = x0 + 1 <= W - 1, y1ok = y0 + 1 <= H - 1;
         const int eo = (h * W + w) * C + cbase + lv * 4;
-        const float* xp = src + ((y0 * W + x0) * C + cbase + lv * 4);
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        // global loads first (pass-through + the 4 taps of x), then the staged 3x3 gather
-        const float4 pass = __ldg(reinterpret_cast<const float4*>(gpass + eo));
-        const float4 xa = __ldg(reinterpret_cast<const float4*>(xp));
-        const float4 xb = x1ok ? __ldg(reinterpret_cast<const float4*>(xp + C)) : zero4;
-        const float4 xc = y1ok ? __ldg(reinterpret_cast<const float4*>(xp + rowC)) : zero4;
-        const float4 xd = (x1ok && y1ok) ? __ldg(reinterpret_cast<const float4*>(xp + rowC + C)) : zero4;
+        if constexpr (!PF) {
+          const int x0 = (int)x0f, y0 = (int)y0f;
+          const bool x1ok = x0 + 1 <= W - 1, y1ok = y0 + 1 <= H - 1;
+          const float* xp = src + ((y0 * W + x0) * C + cbase + lv * 4);
+          const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          // global loads first (pass-through + the 4 taps of x), then the staged 3x3 gather
+          pass = __ldg(reinterpret_cast<const float4*>(gpass + eo));
+          xa = __ldg(reinterpret_cast<const float4*>(xp));
+          xb = x1ok ? __ldg(reinterpret_cast<const float4*>(xp + C)) : zero4;
+          xc = y1ok ? __ldg(reinterpret_cast<const float4*>(xp + rowC)) : zero4;
+          xd = (x1ok && y1ok) ? __ldg(reinterpret_cast<const float4*>(xp + rowC + C)) : zero4;
+        }
         const float4* gc = gws + ((hl + 1) * TILE_W2 + wl + 1) * LC + lv;        // own pixel in the staged tile
         const float wgt[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, w8};
         const float4 g = gc[0];                              // own pixel: the source-side gradient
@@ -1053,22 +1101,28 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
       // measured on B200 (benchmarks/bwd_probe.py, 4 CTAs per SM): 4-row tiles for >= 32 channels, 8-row tiles below
       if (R <= 0) R = lshift == 3 ? 4 : 8;
       if (R > H) R = H;
-      const size_t smem = tile_smem_bytes(R, 1 << lshift);
-      if (smem <= 72 * 1024 && (int64_t)HW * C < (1ll << 31)) {
+      // next item's x taps prefetched through shared-memory slots (knob ndhwc_bwd_pf: -1 auto, 0 off, 1 on).  Measured on
+      // B200 (benchmarks/bwd_probe.py): +4 % / +11 % at C = 128 / 256 (many 32-channel chunks per tile: the prefetch runs
+      // across the chunk boundaries), -7 % at C <= 64 (3 instead of 4 CTAs per SM) => auto = C >= 128
+      const int pfo = option(OPT_NDHWC_BWD_PF);
+      const bool pfv = pfo < 0 ? C >= 128 : pfo != 0;
+      const size_t smem = tile_smem_bytes(R, 1 << lshift) + (pfv ? TILE_SLOT_BYTES : 0);
+      if (smem <= 104 * 1024 && (int64_t)HW * C < (1ll << 31)) {
         const int tiles_x = (W + TILE_W - 1) / TILE_W, tiles_y = (H + R - 1) / R;
         const unsigned tgrid = (unsigned)(tiles_x * tiles_y * 2 * B);
         // optional caller workspace (>= 64 B, 16 B aligned): word 0 carries the far-tap epoch stamp of this call
         static std::atomic<int> g_epoch{0};
         int* far_flag = (ws != nullptr && ws_bytes >= 64 && aligned16(ws)) ? reinterpret_cast<int*>(ws) : nullptr;
         const int epoch = g_epoch.fetch_add(1, std::memory_order_relaxed) + 1;
-#define SMOW_TILE_LAUNCH(CT, WT)                                                                                     \
+#define SMOW_TILE_LAUNCH2(CT, WT, PFV)                                                                                \
   do {                                                                                                               \
     if (smem > 48 * 1024)                                                                                            \
-      cudaFuncSetAttribute(warp_bwd_ndhwc_tile_kernel<CT, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024); \
-    warp_bwd_ndhwc_tile_kernel<CT, WT><<<tgrid, 256, smem, st>>>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, C, \
+      cudaFuncSetAttribute(warp_bwd_ndhwc_tile_kernel<CT, WT, PFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024); \
+    warp_bwd_ndhwc_tile_kernel<CT, WT, PFV><<<tgrid, 256, smem, st>>>(gout, x1, x2, sB, flow, xs, ys, gx1, gx2, gflow, C, \
                                                                  H, W, lshift, R, tiles_x, tiles_y, ilog2_exact(W), \
                                                                  ilog2_exact(H), far_flag, epoch);                   \
   } while (0)
+#define SMOW_TILE_LAUNCH(CT, WT) do { if (pfv) SMOW_TILE_LAUNCH2(CT, WT, true); else SMOW_TILE_LAUNCH2(CT, WT, false); } while (0)
         // compile-time (C, W) for the models' shapes (C = 16 / 32 at 128 x 128) and the sweep's; anything else is generic
         bool done = false;
 #define SMOW_TILE_CASE(CT, WT) if (!done && C == CT && W == WT) { SMOW_TILE_LAUNCH(CT, WT); done = true; }
@@ -1078,6 +1132,7 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
         if (!done) SMOW_TILE_LAUNCH(0, 0);
 #undef SMOW_TILE_CASE
 #undef SMOW_TILE_LAUNCH
+#undef SMOW_TILE_LAUNCH2
         const int64_t pf = (int64_t)HW * 2 * B;
         const int fcap = device_info().sms * 4;       // grid-stride: a small grid exits fastest when there is no far tap
         const int fgrid = (int)((pf + 255) / 256 < fcap ? (pf + 255) / 256 : fcap);
