@@ -346,6 +346,29 @@ def test_warp_ndhwc_tile_gather_backward(sigma, variants):
     check_warp(a, torch_ref.warp_with_grads(x, flow, gout))
 
 
+@pytest.mark.parametrize("case", [(2, 16, 128, 128, 0.3), (1, 64, 40, 72, 0.4), (1, 256, 32, 32, 0.3), (2, 128, 33, 65, 0.5),
+                                  (1, 8, 37, 52, 0.3), (1, 32, 5, 7, 0.2)])
+def test_warp_ndhwc_tile_gather_tap_prefetch_is_bit_identical(case, variants):
+    """Knob ndhwc_bwd_pf: the variant of the tile gather that prefetches the next item's x taps into shared-memory slots
+    (auto for C >= 128) performs the same arithmetic in the same order as the plain one: gx and gflow are bit-identical
+    (sub-pixel flows: no float atomics involved), and both match the same-device reference."""
+    B, C, H, W, sigma = case
+    g = torch.Generator(device=DEV).manual_seed(C * 7 + W)
+    x = torch.randn(B, C, 2, H, W, device=DEV, generator=g).contiguous(memory_format=CL3)
+    flow = (torch.randn(B, 2, 2, H, W, device=DEV, generator=g) * sigma).clamp(-0.9, 0.9)
+    gout = torch.randn(B, C, 4, H, W, device=DEV, generator=g).contiguous(memory_format=CL3)
+    saved = _lib.get_option("ndhwc_bwd_pf")
+    try:
+        res = {}
+        for pf in (0, 1):
+            _lib.set_option("ndhwc_bwd_pf", pf)
+            res[pf] = run_warp(x, flow, gout)
+    finally:
+        _lib.set_option("ndhwc_bwd_pf", saved)
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    check_warp(res[1], torch_ref.warp_with_grads(x, flow, gout))
+
+
 @pytest.mark.parametrize("sigma", [0.5, 8.0])
 @pytest.mark.parametrize("case", [(2, 16, 64, 64), (1, 64, 40, 72), (1, 256, 16, 32), (2, 32, 128, 128)])
 def test_warp_ndhwc_bf16_storage_forward_and_backward(case, sigma):
