@@ -18,6 +18,7 @@ F32, BF16, ND = _lib.F32, _lib.BF16, _lib.NDHWC
 CASES = [
     ("warp_stack_fwd", {"B": B, "C": C, "H": H, "W": H, "dtype": F32, "layout": ND, "pair": 0}),
     ("warp_stack_bwd", {"B": B, "C": C, "H": H, "W": H, "dtype": F32, "layout": ND, "pair": 0}),
+    ("warp_stack_bwd", {"B": 16, "C": 128, "H": H, "W": H, "dtype": F32, "layout": ND, "pair": 0}),
     ("warp_stack_fwd", {"B": B, "C": 64, "H": H, "W": H, "dtype": BF16, "layout": ND, "pair": 0}),
     ("warp_stack_bwd", {"B": B, "C": 64, "H": H, "W": H, "dtype": BF16, "layout": ND, "pair": 0}),
     ("tlerp_cat_fwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 1}),
@@ -26,6 +27,8 @@ CASES = [
     ("tlerp_cat_bwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 2}),
     ("tokenizer_fwd", {"B": B, "C": C, "hw": H * H}),
     ("tokenizer_bwd", {"B": B, "C": C, "hw": H * H}),
+    ("tokenizer_fwd", {"B": B, "C": 16, "hw": H * H}),
+    ("tokenizer_bwd", {"B": B, "C": 16, "hw": H * H}),
     ("frame_mix_fwd", {"B": B, "C": C, "T": 4, "hw": H * H, "tc": 1}),
     ("frame_mix_bwd", {"B": B, "C": C, "T": 4, "hw": H * H, "tc": 1}),
     ("frame_mix_wgrad", {"B": B, "C": C, "T": 4, "hw": H * H, "tc": 1}),

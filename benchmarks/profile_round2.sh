@@ -16,7 +16,7 @@ timeout 900 ncu --set full --clock-control none --profile-from-start off -k "$K"
 echo "in-step full rc=$?"
 ncu -i /tmp/r2_instep_kernels.ncu-rep --page raw --csv > gpurun_out/r2_instep_kernels.csv 2>/dev/null
 timeout 200 python benchmarks/one_kernel_r2.py > gpurun_out/r2_one_plain.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --profile-from-start off -k "$K" -c 70 -o /tmp/r2_cold_kernels -f python benchmarks/one_kernel_r2.py > gpurun_out/r2_one_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --profile-from-start off -k "$K" -c 80 -o /tmp/r2_cold_kernels -f python benchmarks/one_kernel_r2.py > gpurun_out/r2_one_ncu.log 2>&1
 echo "cold full rc=$?"
 ncu -i /tmp/r2_cold_kernels.ncu-rep --page raw --csv > gpurun_out/r2_cold_kernels.csv 2>/dev/null
 cat gpurun_out/r2_one_plain.log

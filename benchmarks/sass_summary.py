@@ -16,7 +16,7 @@ LIB = os.path.join(ROOT, "smow_net_b200", "libsmow_b200.so")
 COLS = [("UTCHMMA", "tcgen05.mma (5th-gen tensor cores)"), ("LDTM", "tcgen05.ld (TMEM -> registers)"),
         ("UTMALDG", "TMA tensor-map load"), ("UTMASTG", "TMA tensor-map store"), ("UBLKCP", "1-D bulk copy (cp.async.bulk)"),
         ("UBLKPF", "bulk L2 prefetch"), ("LDGSTS", "cp.async (16-byte async copy)"), ("SYNCS", "mbarrier ops"),
-        ("FFMA2", "packed fp32x2 FMA"), ("FFMA", "fp32 FMA (incl. FFMA2)"), ("HMMA", "legacy mma.sync"),
+        ("FFMA2", "packed fp32x2 FMA"), ("FFMA", "fp32 FMA (incl. FFMA2)"), ("HMMA", "warp-level mma.sync (the 8-token-wide tokenizer GEMMs, 3xTF32)"),
         ("REDG", "global reductions (red.global.add)"), ("ATOMG", "global atomics"), ("LDG", "global loads"), ("STG", "global stores"),
         ("LDS", "shared loads"), ("STS", "shared stores"), ("SHFL", "warp shuffles")]
 
@@ -52,6 +52,8 @@ def main():
         f.write("| **all %d kernels** | %d | %s |\n" % (len(kernels), tot["_total"], " | ".join(str(tot[p]) for p, _ in COLS)))
         tc = [n for n, c in kernels.items() if c["UTCHMMA"]]
         f.write("\nKernels with tcgen05.mma (`UTCHMMA`) + TMEM loads (`LDTM`) + TMA (`UTMALDG` / `UTMASTG`): %s.\n" % ", ".join("`%s`" % n for n in tc))
+        hm = [n for n, c in kernels.items() if c["HMMA"]]
+        f.write("\nKernels with warp-level TF32 MMAs (`HMMA.1688.F32.TF32`; N = 8 tokens is below a tcgen05 tile): %s.\n" % ", ".join("`%s`" % n for n in hm))
     print(out)
 
 
