@@ -201,7 +201,7 @@ def roofline_block(calls, step_ms, device, n_steps_recorded):
     for name, k in per_kernel.items():
         k["achieved_GB_per_s"] = k["bytes_per_step"] / k["ms_per_step"] / 1e6
         k["frac"] = k["achieved_GB_per_s"] / peak
-        k["row"] = ("N2" if name.startswith("tokenizer") else "N4" if name.startswith("frame_mix") else
+        k["row"] = ("A1+N2" if name.startswith("warp_tokens") else "N2" if name.startswith("tokenizer") else "N4" if name.startswith("frame_mix") else
                     "N1" if name.startswith("flow_head") else "A1-A5")
     dom_name = max(per_kernel, key=lambda n: per_kernel[n]["ms_per_step"])
     dom_rows = [r for r in rows if r["kernel"] == dom_name]

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SMOW_ABI_VERSION 8
+#define SMOW_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define SMOW_API __attribute__((visibility("default")))
@@ -206,6 +206,31 @@ SMOW_API int smow_tokenizer_bwd(const float* gtokens, const void* x, const float
                        const float* tokens, const float* stats,
                        void* gx, float* gwa, float* gba, int B, int C, int64_t hw,
                        int dtype, int layout, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- A1 + N2 fused: the warped stack never reaches HBM -------------------------------------------
+ * The tokenizer is the only consumer of OFW's output (models/SMOW_Net.py:50-52 -> :176-187; LW :48 -> :195-206), so
+ * tokens = tokenizer(flow_warp(x, flow)) is ONE pass over the two input frames: every chunk kernel stages its pixel
+ * rows itself — frames 0 / 3 are bulk copies of x[:, :, 0] / x[:, :, 1], frames 1 / 2 are warped into shared memory
+ * with the arithmetic of smow_warp_stack_fwd (same coordinate chain, same tap order: the staged rows are bit-identical
+ * to what that launch writes) — and feeds them to the tensor-core tokenizer.  HBM traffic forward: x read once per
+ * frame it feeds (2 * 2*C*HW*4 B) + flow, instead of warp (6*C*HW*4) + tokenizer (4*C*HW*4).
+ *   x (B,C,2,H,W) fp32 NDHWC, flow (B,2,2,H,W), xs / ys as for smow_warp_stack_fwd; C = 16 / 32 (the two models;
+ *   smow_warp_tokenizer_supported(C) != 0, which also requires knob "tok_variant" != 0); tokens (B,4,8,C), stats (B,4,16),
+ *   workspace: smow_tokenizer_workspace_bytes(B, C, H*W).
+ * Backward: the staged rows are re-computed the same way (nothing was saved but x, flow, tokens, stats); gstack
+ *   (B,C,4,H,W) NDHWC receives d loss / d stack — the `gout` of smow_warp_stack_bwd, which then yields gx and gflow;
+ *   gwa (8,C), gba (8) overwritten.                                                                  */
+SMOW_API int smow_warp_tokenizer_supported(int C);
+SMOW_API int smow_warp_tokenizer_fwd(const void* x, const float* flow, const float* xs, const float* ys,
+                       const float* wa, const float* ba, float* tokens, float* stats,
+                       int B, int C, int H, int W, int dtype, int layout,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+SMOW_API int smow_warp_tokenizer_bwd(const float* gtokens, const void* x, const float* flow,
+                       const float* xs, const float* ys, const float* wa, const float* ba,
+                       const float* tokens, const float* stats,
+                       void* gstack, float* gwa, float* gba,
+                       int B, int C, int H, int W, int dtype, int layout,
+                       void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- N4: cyclic temporal frame mix of the decoder blocks -------------------------------------
  * Replaces, for C_in = C_out = C in {16, 28, 32, 64} (the large decoder levels), the slice / ten 1x1x1

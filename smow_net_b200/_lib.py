@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmow_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 F32, BF16 = 0, 1
 NCDHW, NDHWC = 0, 1
 
@@ -43,6 +43,10 @@ SIGNATURES = {
     "smow_tokenizer_workspace_bytes": (_i64, [_i, _i, _i64]),
     "smow_tokenizer_fwd": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i64, _i, _i, _vp, _i64, _vp]),
     "smow_tokenizer_bwd": (_i, [_fp, _vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i64, _i, _i, _vp, _i64, _vp]),
+    "smow_warp_tokenizer_supported": (_i, [_i]),
+    "smow_warp_tokenizer_fwd": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "smow_warp_tokenizer_bwd": (_i, [_fp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i,
+                                     _vp, _i64, _vp]),
     "smow_frame_mix_supported": (_i, [_i]),
     "smow_frame_mix_apply": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i64, _i, _i, _vp]),
     "smow_frame_mix_wgrad_workspace_bytes": (_i64, [_i, _i, _i64]),

@@ -440,7 +440,7 @@ int smow_tokenizer_fwd(const void* x, const float* wa, const float* ba, float* t
   tok_allow_smem(tok_fwd_chunk_kernel<CG, ITER>, smem);       \
   tok_fwd_chunk_kernel<CG, ITER><<<grid, TOK_FWD_THREADS, smem, st>>>((const float*)x, wa, ba, part, g)
   // pixels per thread = chunk * LP / threads: 8 for C <= 16 (512-pixel chunks, 4 lanes per pixel), 16 beyond
-  if (mma) tok_fwd_mma_launch((const float*)x, wa, ba, part, g, B, st);
+  if (mma) tok_fwd_mma_launch((const float*)x, nullptr, wa, ba, part, g, B, st);
   else switch (C / g.G) {
     case 4: SMOW_TOK_FWD(4, 8); break;
     case 8: SMOW_TOK_FWD(8, 8); break;
@@ -468,7 +468,7 @@ int smow_tokenizer_bwd(const float* gtokens, const void* x, const float* wa, con
 #define SMOW_TOK_BWD(CG)                                 \
   tok_allow_smem(tok_bwd_chunk_kernel<CG>, smem);        \
   tok_bwd_chunk_kernel<CG><<<grid, TOK_BWD_THREADS, smem, st>>>(gtokens, (const float*)x, wa, ba, tokens, stats, (float*)gx, part, g)
-  if (mma) tok_bwd_mma_launch(gtokens, (const float*)x, wa, ba, tokens, stats, (float*)gx, part, g, B, st);
+  if (mma) tok_bwd_mma_launch(gtokens, (const float*)x, nullptr, wa, ba, tokens, stats, (float*)gx, part, g, B, st);
   else switch (C / g.G) {
     case 4: SMOW_TOK_BWD(4); break;
     case 8: SMOW_TOK_BWD(8); break;
@@ -478,6 +478,57 @@ int smow_tokenizer_bwd(const float* gtokens, const void* x, const float* wa, con
   tok_bwd_combine_kernel<<<TOK_L * C + TOK_L, 256, 0, st>>>(part, gwa, gba, 4 * B * g.nchunks, C);
   count_launch(2);
   return check_launch("tokenizer_bwd");
+}
+
+// ---- rows A1 + N2 fused: OFW.flow_warp -> Transformer_Encoder's pooling without the stack in HBM -------------------------
+static int warp_tok_geom(TokGeom& g, TokWarpSrc& src, const void* x, const float* flow, const float* xs, const float* ys,
+                         int B, int C, int H, int W, int dtype, int layout) {
+  if (H <= 0 || W <= 0) return fail(SMOW_EINVAL, "warp_tokenizer: bad shape");
+  if (int rc = tok_geom(g, B, C, (int64_t)H * W, x, dtype, layout)) return rc;
+  if (!flow || !xs || !ys) return fail(SMOW_EINVAL, "warp_tokenizer: null pointer");
+  if (!tok_use_mma(C))
+    return fail(SMOW_EDTYPE, "warp_tokenizer: built on the tensor-core tokenizer kernels (C = 16 / 32, tok_variant != 0)");
+  if ((int64_t)B * 4 * H * W * C >= ((int64_t)1 << 31)) return fail(SMOW_ERANGE, "warp_tokenizer: tensor too large for 32-bit tile indexing");
+  src.x = (const float*)x; src.flow = flow; src.xs = xs; src.ys = ys; src.H = H; src.W = W; src.wshift = -1;
+  for (int s = 0; s < 31; ++s) if ((1 << s) == W) src.wshift = s;
+  return 0;
+}
+
+int smow_warp_tokenizer_supported(int C) { return tok_use_mma(C) ? 1 : 0; }
+
+int smow_warp_tokenizer_fwd(const void* x, const float* flow, const float* xs, const float* ys, const float* wa,
+                            const float* ba, float* tokens, float* stats, int B, int C, int H, int W, int dtype,
+                            int layout, void* ws, int64_t ws_bytes, void* stream) {
+  TokGeom g;
+  TokWarpSrc src;
+  if (int rc = warp_tok_geom(g, src, x, flow, xs, ys, B, C, H, W, dtype, layout)) return rc;
+  if (!wa || !ba || !tokens || !stats) return fail(SMOW_EINVAL, "warp_tokenizer: null pointer");
+  if (!ws || ws_bytes < smow_tokenizer_workspace_bytes(B, C, g.hw) || !aligned16(ws))
+    return fail(SMOW_EINVAL, "warp_tokenizer: workspace of smow_tokenizer_workspace_bytes() bytes required");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(ws);
+  tok_fwd_mma_launch(nullptr, &src, wa, ba, part, g, B, st);
+  tok_fwd_combine_kernel<<<(4 * B * TOK_L + 7) / 8, 256, 0, st>>>(part, tokens, stats, g, 4 * B);
+  count_launch(2);
+  return check_launch("warp_tokenizer_fwd");
+}
+
+int smow_warp_tokenizer_bwd(const float* gtokens, const void* x, const float* flow, const float* xs, const float* ys,
+                            const float* wa, const float* ba, const float* tokens, const float* stats, void* gstack,
+                            float* gwa, float* gba, int B, int C, int H, int W, int dtype, int layout, void* ws,
+                            int64_t ws_bytes, void* stream) {
+  TokGeom g;
+  TokWarpSrc src;
+  if (int rc = warp_tok_geom(g, src, x, flow, xs, ys, B, C, H, W, dtype, layout)) return rc;
+  if (!gtokens || !wa || !ba || !tokens || !stats || !gstack || !gwa || !gba) return fail(SMOW_EINVAL, "warp_tokenizer: null pointer");
+  if (!ws || ws_bytes < smow_tokenizer_workspace_bytes(B, C, g.hw) || !aligned16(ws) || !aligned16(gstack))
+    return fail(SMOW_EINVAL, "warp_tokenizer: workspace of smow_tokenizer_workspace_bytes() bytes required");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = reinterpret_cast<float*>(ws);
+  tok_bwd_mma_launch(gtokens, nullptr, &src, wa, ba, tokens, stats, (float*)gstack, part, g, B, st);
+  tok_bwd_combine_kernel<<<TOK_L * C + TOK_L, 256, 0, st>>>(part, gwa, gba, 4 * B * g.nchunks, C);
+  count_launch(2);
+  return check_launch("warp_tokenizer_bwd");
 }
 
 }  // extern "C"

@@ -66,15 +66,110 @@ __device__ __forceinline__ void zero_dead_rows(float* xs, int n, int chunk, int 
   for (int i = n * C + threadIdx.x; i < chunk * C; i += nthreads) xs[i] = 0.f;
 }
 
+// ---- fused staging (rows A1 + N2) -------------------------------------------------------------------------------------------
+// Frame f of pair b as the kernels see it: f = 0 / 3 are the input frames themselves, f = 1 / 2 their warps (reference
+// models/SMOW_Net.py:634-636).  stage_warped_rows writes the warped rows [p0, p0 + n) of frame 1 + t into shared memory —
+// what warp_fwd_ndhwc_shfl_kernel would have written to HBM, bit for bit: a warp owns 32 consecutive pixels, lane l runs the
+// reference's coordinate chain for pixel l once, then in Q steps every lane serves one (pixel, 4-channel vector) with the
+// footprint fetched by indexed shuffles: 4 tap gathers, FMAs in ATen's order (nw, ne, sw, se; out-of-bounds taps skipped).
+// Rows >= n (ragged last chunk) are written as zeros.
+template <int C, int CHUNK, int NT>
+__device__ __forceinline__ void stage_warped_rows(float* __restrict__ rows, const TokWarpSrc& s, int b, int t, int p0, int n) {
+  constexpr int Q = C / 4, QSHIFT = Q == 4 ? 2 : 3, PPW = 32 / Q, GPW = (CHUNK / 32) / (NT / 32);
+  static_assert(Q == 4 || Q == 8, "C = 16 / 32");
+  static_assert(GPW * (NT / 32) * 32 == CHUNK, "whole 32-pixel groups per warp");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = s.H * s.W, W = s.W;
+  const int v = lane & (Q - 1), sub = lane >> QSHIFT;
+  const float* src = s.x + (int64_t)(b * 2 + t) * HW * C + v * 4;
+  const float* fl = s.flow + ((int64_t)(b * 2) * 2 + t) * HW;
+  // the warp's GPW groups are independent: all flow loads first, then the chains, then the gathers of one group at a time
+  // (16 / 32 independent 16-byte loads in flight per thread) — the staging is latency bound, not bandwidth bound
+  float fx[GPW], fy[GPW];
+#pragma unroll
+  for (int k = 0; k < GPW; ++k) {
+    const int pl = (warp * GPW + k) * 32 + lane;
+    const bool live = pl < n;
+    fx[k] = live ? __ldg(fl + p0 + pl) : 0.f;
+    fy[k] = live ? __ldg(fl + p0 + pl + 2 * (int64_t)HW) : 0.f;
+  }
+  int own_o[GPW], own_flags[GPW];
+  float own_nw[GPW], own_ne[GPW], own_sw[GPW], own_se[GPW];
+#pragma unroll
+  for (int k = 0; k < GPW; ++k) {
+    const int pl = (warp * GPW + k) * 32 + lane;
+    const int p = pl < n ? p0 + pl : p0;                        // dead lanes: any valid pixel (their rows are zeroed below)
+    const int h = s.wshift >= 0 ? (p >> s.wshift) : (p / W), w = p - h * W;
+    const Footprint fp = footprint_auto(__ldg(s.xs + w), __ldg(s.ys + h), fx[k], fy[k], W, s.H);
+    own_nw[k] = __fmul_rn(fp.wx0, fp.wy0); own_ne[k] = __fmul_rn(fp.wx1, fp.wy0);
+    own_sw[k] = __fmul_rn(fp.wx0, fp.wy1); own_se[k] = __fmul_rn(fp.wx1, fp.wy1);
+    own_o[k] = fp.y0 * W + fp.x0;
+    own_flags[k] = (fp.x1ok ? 1 : 0) | (fp.y1ok ? 2 : 0);
+  }
+#pragma unroll
+  for (int k = 0; k < GPW; ++k) {
+    const int g0 = (warp * GPW + k) * 32;
+    float4 r[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+      const int sl = j * PPW + sub;                               // lane that holds this pixel's footprint
+      const int o_nw = __shfl_sync(0xffffffffu, own_o[k], sl), flags = __shfl_sync(0xffffffffu, own_flags[k], sl);
+      const float nw = __shfl_sync(0xffffffffu, own_nw[k], sl), ne = __shfl_sync(0xffffffffu, own_ne[k], sl);
+      const float sw = __shfl_sync(0xffffffffu, own_sw[k], sl), se = __shfl_sync(0xffffffffu, own_se[k], sl);
+      r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g0 + sl < n) {
+        const float* tp = src + (int64_t)o_nw * C;
+        // taps outside the image are re-pointed at the nw tap (always in bounds) and dropped from the sum: four
+        // unconditional loads in flight instead of three dependent branches
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tp));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(tp + ((flags & 1) ? C : 0)));
+        const float4 c2 = __ldg(reinterpret_cast<const float4*>(tp + ((flags & 2) ? (int64_t)W * C : 0)));
+        const float4 c3 = __ldg(reinterpret_cast<const float4*>(tp + (flags == 3 ? (int64_t)(W + 1) * C : 0)));
+        float4 q;
+        q.x = __fmul_rn(a.x, nw); q.y = __fmul_rn(a.y, nw); q.z = __fmul_rn(a.z, nw); q.w = __fmul_rn(a.w, nw);
+        if (flags & 1) { q.x = fmaf(c1.x, ne, q.x); q.y = fmaf(c1.y, ne, q.y); q.z = fmaf(c1.z, ne, q.z); q.w = fmaf(c1.w, ne, q.w); }
+        if (flags & 2) { q.x = fmaf(c2.x, sw, q.x); q.y = fmaf(c2.y, sw, q.y); q.z = fmaf(c2.z, sw, q.z); q.w = fmaf(c2.w, sw, q.w); }
+        if (flags == 3) { q.x = fmaf(c3.x, se, q.x); q.y = fmaf(c3.y, se, q.y); q.z = fmaf(c3.z, se, q.z); q.w = fmaf(c3.w, se, q.w); }
+        r[j] = q;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < Q; ++j) *reinterpret_cast<float4*>(rows + (g0 + j * PPW + sub) * C + v * 4) = r[j];
+  }
+}
+
+// Stage the chunk [p0, p0 + n) of stack frame bk = 4 b + f into `rows`.  Plain form: one bulk copy out of the stack.  Fused
+// form: bulk copy out of input frame 0 / 1 for f = 0 / 3, warp for f = 1 / 2.  Returns true when the caller has to wait on
+// `bar` (a bulk copy is in flight) after the CTA-wide barrier both forms need (mbarrier initialised / rows written).
+template <int C, int CHUNK, int NT, bool FUSED>
+__device__ __forceinline__ bool stage_chunk(float* rows, uint64_t* bar, const float* __restrict__ x, const TokWarpSrc& s,
+                                            int bk, int p0, int n, int64_t hw) {
+  const int f = bk & 3;
+  const bool warped = FUSED && (f == 1 || f == 2);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    if (!warped) {
+      const float* from = FUSED ? s.x + ((int64_t)((bk >> 2) * 2 + (f == 3 ? 1 : 0)) * hw + p0) * C
+                                : x + ((int64_t)bk * hw + p0) * C;
+      mbar_expect_tx(bar, (uint32_t)n * C * 4u);
+      bulk_g2s(rows, from, (uint32_t)n * C * 4u, bar);
+    }
+  }
+  if (warped) stage_warped_rows<C, CHUNK, NT>(rows, s, bk >> 2, f - 1, p0, n);
+  else if (n < CHUNK) zero_dead_rows(rows, n, CHUNK, C, NT);
+  return !warped;
+}
+
 // ---- forward -----------------------------------------------------------------------------------------------------------
 // grid (nchunks, 4*B), 8 warps, one chunk per CTA (several CTAs per SM overlap each other's staging: a persistent,
 // double-buffered variant with fewer resident warps measured 10-20 % slower — the kernels are bound by the latency of their
 // dependent MMA / shared-memory chains, not by the copy).  Warp w owns pixels [w*PW, (w+1)*PW) of the chunk, PW = CHUNK / 8,
 // in groups of 8.  Softmax statistics are warp-local (max over the warp's pixels), merged once per CTA.
-template <int C, int CHUNK>
+template <int C, int CHUNK, bool FUSED>
 __global__ void __launch_bounds__(TOKM_FWD_THREADS)
-tok_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ wa, const float* __restrict__ ba,
-                   float* __restrict__ part, TokGeom geo) {
+tok_fwd_mma_kernel(const float* __restrict__ x, const TokWarpSrc src, const float* __restrict__ wa,
+                   const float* __restrict__ ba, float* __restrict__ part, TokGeom geo) {
   constexpr int NT = TOKM_FWD_THREADS, NW = NT / 32, PW = CHUNK / NW, NG = PW / 8;
   __shared__ uint64_t bar;
   extern __shared__ __align__(16) float dyn[];            // [CHUNK][C] staged rows | per-warp partials
@@ -83,20 +178,17 @@ tok_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ wa, co
   float* mw = tw + NW * TOK_L * C;                        // [NW][8]
   float* sw = mw + NW * TOK_L;                            // [NW][8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int bk = blockIdx.y, p0 = blockIdx.x * CHUNK;
+  // fused form: the CTAs that warp (frames 1, 2) are the long ones and are dispatched first (frame order 1, 2, 3, 0)
+  const int nb = gridDim.y >> 2;
+  const int bk = FUSED ? 4 * (int)(blockIdx.y % nb) + (((int)(blockIdx.y / nb) + 1) & 3) : (int)blockIdx.y;
+  const int p0 = blockIdx.x * CHUNK;
   const int n = (int64_t)p0 + CHUNK < geo.hw ? CHUNK : (int)(geo.hw - p0);
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    mbar_fence_init();
-    mbar_expect_tx(&bar, (uint32_t)n * C * 4u);
-    bulk_g2s(dyn, x + ((int64_t)bk * geo.hw + p0) * C, (uint32_t)n * C * 4u, &bar);
-  }
-  if (n < CHUNK) zero_dead_rows(dyn, n, CHUNK, C, NT);
+  const bool copied = stage_chunk<C, CHUNK, NT, FUSED>(dyn, &bar, x, src, bk, p0, n, geo.hw);
   uint32_t wf[C / 8][4];
   load_row_frags<C>(wf, wa, g, t);
   const float bias = __ldg(ba + g);
-  __syncthreads();                                        // barrier initialised, dead rows zeroed
-  mbar_wait(&bar, 0);
+  __syncthreads();                                        // barrier initialised, dead rows zeroed / warped rows written
+  if (copied) mbar_wait(&bar, 0);
   const int wbase = warp * PW;
   {
     // phase 1: logits of the warp's pixels (kept in registers) and their maximum per token
@@ -185,9 +277,10 @@ tok_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ wa, co
 
 // ---- backward ----------------------------------------------------------------------------------------------------------
 // grid (nchunks, 4*B), 4 warps; warp w owns pixels [w*PW, (w+1)*PW), 16 per iteration (two 8-pixel groups A, B).
-template <int C, int CHUNK>
+template <int C, int CHUNK, bool FUSED>
 __global__ void __launch_bounds__(TOKM_BWD_THREADS, 4)
-tok_bwd_mma_kernel(const float* __restrict__ gtok, const float* __restrict__ x, const float* __restrict__ wa,
+tok_bwd_mma_kernel(const float* __restrict__ gtok, const float* __restrict__ x, const TokWarpSrc src,
+                   const float* __restrict__ wa,
                    const float* __restrict__ ba, const float* __restrict__ tokens, const float* __restrict__ stats,
                    float* __restrict__ gx, float* __restrict__ part, TokGeom geo) {
   constexpr int NT = TOKM_BWD_THREADS, NW = NT / 32, PW = CHUNK / NW, NI = PW / 16;
@@ -199,15 +292,12 @@ tok_bwd_mma_kernel(const float* __restrict__ gtok, const float* __restrict__ x, 
   float* dww = dyn + CHUNK * C + (C / 8) * 2 * 32 * 4;    // [NW][8][C]
   float* dbw = dww + NW * TOK_L * C;                      // [NW][8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int bk = blockIdx.y, p0 = blockIdx.x * CHUNK;
+  // fused form: the CTAs that warp (frames 1, 2) are the long ones and are dispatched first (frame order 1, 2, 3, 0)
+  const int nb = gridDim.y >> 2;
+  const int bk = FUSED ? 4 * (int)(blockIdx.y % nb) + (((int)(blockIdx.y / nb) + 1) & 3) : (int)blockIdx.y;
+  const int p0 = blockIdx.x * CHUNK;
   const int n = (int64_t)p0 + CHUNK < geo.hw ? CHUNK : (int)(geo.hw - p0);
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    mbar_fence_init();
-    mbar_expect_tx(&bar, (uint32_t)n * C * 4u);
-    bulk_g2s(dyn, x + ((int64_t)bk * geo.hw + p0) * C, (uint32_t)n * C * 4u, &bar);
-  }
-  if (n < CHUNK) zero_dead_rows(dyn, n, CHUNK, C, NT);
+  const bool copied = stage_chunk<C, CHUNK, NT, FUSED>(dyn, &bar, x, src, bk, p0, n, geo.hw);
   // B operand of GEMM3 in fragment order: n-tile j, column n = g <-> channel 16(j>>1) + 4(g>>1) + 2(j&1) + (g&1), so that a
   // thread's accumulators of n-tiles 2q, 2q+1 are the 4 consecutive channels 16q + 4t .. +3 of its pixel.
   // k-step 0: attn x gtok (per pair-frame), k-step 1: dlogit x W (constant)
@@ -243,7 +333,7 @@ tok_bwd_mma_kernel(const float* __restrict__ gtok, const float* __restrict__ x, 
   const bool odd = g & 1;
   __syncthreads();                                        // barrier initialised, dead rows zeroed, V fragments and D ready
   const float D = dsum[g];
-  mbar_wait(&bar, 0);
+  if (copied) mbar_wait(&bar, 0);
   {
     float db = 0.f;
     float dwt[C / 16][4];
@@ -365,32 +455,33 @@ template <typename K> static void tokm_allow_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-void tok_fwd_mma_launch(const float* x, const float* wa, const float* ba, float* part, const TokGeom& g, int B,
-                        cudaStream_t st) {
+void tok_fwd_mma_launch(const float* x, const TokWarpSrc* src, const float* wa, const float* ba, float* part,
+                        const TokGeom& g, int B, cudaStream_t st) {
   const dim3 grid(g.nchunks, 4 * B);
   const int NW = TOKM_FWD_THREADS / 32;
   const size_t smem = ((size_t)g.chunk * g.C + (size_t)NW * (TOK_L * g.C + 2 * TOK_L)) * sizeof(float);
-  if (g.C == 16) {
-    tokm_allow_smem(tok_fwd_mma_kernel<16, 512>, smem);
-    tok_fwd_mma_kernel<16, 512><<<grid, TOKM_FWD_THREADS, smem, st>>>(x, wa, ba, part, g);
-  } else {
-    tokm_allow_smem(tok_fwd_mma_kernel<32, 512>, smem);
-    tok_fwd_mma_kernel<32, 512><<<grid, TOKM_FWD_THREADS, smem, st>>>(x, wa, ba, part, g);
-  }
+  const TokWarpSrc s = src ? *src : TokWarpSrc{};
+#define SMOW_TOKM_FWD(CC, FU)                                    \
+  tokm_allow_smem(tok_fwd_mma_kernel<CC, 512, FU>, smem);        \
+  tok_fwd_mma_kernel<CC, 512, FU><<<grid, TOKM_FWD_THREADS, smem, st>>>(x, s, wa, ba, part, g)
+  if (g.C == 16) { if (src) { SMOW_TOKM_FWD(16, true); } else { SMOW_TOKM_FWD(16, false); } }
+  else           { if (src) { SMOW_TOKM_FWD(32, true); } else { SMOW_TOKM_FWD(32, false); } }
+#undef SMOW_TOKM_FWD
 }
 
-void tok_bwd_mma_launch(const float* gtok, const float* x, const float* wa, const float* ba, const float* tokens,
-                        const float* stats, float* gx, float* part, const TokGeom& g, int B, cudaStream_t st) {
+void tok_bwd_mma_launch(const float* gtok, const float* x, const TokWarpSrc* src, const float* wa, const float* ba,
+                        const float* tokens, const float* stats, float* gx, float* part, const TokGeom& g, int B,
+                        cudaStream_t st) {
   const dim3 grid(g.nchunks, 4 * B);
   const int NW = TOKM_BWD_THREADS / 32;
   const size_t smem = ((size_t)g.chunk * g.C + (size_t)(g.C / 8) * 2 * 32 * 4 + (size_t)NW * (TOK_L * g.C + TOK_L)) * sizeof(float);
-  if (g.C == 16) {
-    tokm_allow_smem(tok_bwd_mma_kernel<16, 512>, smem);
-    tok_bwd_mma_kernel<16, 512><<<grid, TOKM_BWD_THREADS, smem, st>>>(gtok, x, wa, ba, tokens, stats, gx, part, g);
-  } else {
-    tokm_allow_smem(tok_bwd_mma_kernel<32, 512>, smem);
-    tok_bwd_mma_kernel<32, 512><<<grid, TOKM_BWD_THREADS, smem, st>>>(gtok, x, wa, ba, tokens, stats, gx, part, g);
-  }
+  const TokWarpSrc s = src ? *src : TokWarpSrc{};
+#define SMOW_TOKM_BWD(CC, FU)                                    \
+  tokm_allow_smem(tok_bwd_mma_kernel<CC, 512, FU>, smem);        \
+  tok_bwd_mma_kernel<CC, 512, FU><<<grid, TOKM_BWD_THREADS, smem, st>>>(gtok, x, s, wa, ba, tokens, stats, gx, part, g)
+  if (g.C == 16) { if (src) { SMOW_TOKM_BWD(16, true); } else { SMOW_TOKM_BWD(16, false); } }
+  else           { if (src) { SMOW_TOKM_BWD(32, true); } else { SMOW_TOKM_BWD(32, false); } }
+#undef SMOW_TOKM_BWD
 }
 
 }  // namespace smow

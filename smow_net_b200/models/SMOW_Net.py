@@ -47,7 +47,7 @@ class SMOW_Net(nn.Module):
         x = torch.stack((x1, x2), dim=2)                       # (B,3,2,H,W), reference :40-42
         stem = self.resnet.relu(self.resnet.bn1(self.resnet.conv1(x)))
         skips = [self.Conv3d(stem)]                            # x0 (B,32,2,H/2,W/2)
-        tokens = self.Transformer_Encoder(self.OFW(skips[0]))  # warp -> semantic tokens
+        tokens = self.Transformer_Encoder.from_warp(self.OFW, skips[0])  # warp -> semantic tokens
 
         feat = self.resnet.maxpool(stem)
         for s in (1, 2, 3, 4):

@@ -55,7 +55,7 @@ class SMOW_Net_LW(nn.Module):
                          memory_format=torch.channels_last_3d if x1.is_cuda else torch.contiguous_format)
         x0[:, :, 0] = pyr1[0]
         x0[:, :, 1] = pyr2[0]
-        tokens = self.Transformer_Encoder(self.OFW(x0))
+        tokens = self.Transformer_Encoder.from_warp(self.OFW, x0)
 
         dec = self.MaxPool(ops.tlerp_pair_cat(None, pyr1[4], pyr2[4]))   # reference :71-73
         for k in (1, 2, 3, 4):

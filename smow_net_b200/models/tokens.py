@@ -108,6 +108,16 @@ class Transformer_Encoder(nn.Module):
         self.transformer = Transformer(dim=in_chan * 4, depth=1, heads=heads, dim_head=in_chan * 4,
                                        mlp_dim=in_chan * 4, dropout=0)
 
+    def from_warp(self, ofw, x):
+        """``self(ofw(x))`` — the reference's ``Transformer_Encoder(OFW(x0))`` (models/SMOW_Net.py:50-52) — without the
+        warped stack in HBM where the fused kernels exist (rows A1 + N2: ``ops.warp_tokens``)."""
+        from .. import ops
+        if self.token_len == 8 and ops.warp_tokens_supported(x, self.conv_a.weight):
+            b, c = x.shape[:2]
+            tok = ops.warp_tokens(x, ofw.predict_flow(x), self.conv_a.weight, self.conv_a.bias) + self.pos_embedding.unsqueeze(0)
+            return self.transformer(tok.permute(0, 2, 1, 3).reshape(b, self.token_len, 4 * c))
+        return self(ofw(x))
+
     def forward(self, x):
         b, c, t, h, w = x.shape
         assert t == 4, "The time dimension (t) must be 4."

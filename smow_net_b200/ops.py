@@ -591,6 +591,94 @@ def semantic_tokens(x, weight, bias):
     return _SemanticTokens.apply(x, weight, bias)
 
 
+# ----------------------------------------------------------------------------- A1 + N2 fused: warp -> tokens
+def warp_tokens_fwd_bytes(B, C, H, W, s=4):
+    """Algorithmic bytes of the fused pass: each input frame feeds two stack frames (itself and its warp), the stack itself
+    never exists: 2 x (2*C*HW*s) read + the flow + the tokens."""
+    return B * (4 * C * H * W * s + 16 * H * W + 4 * 8 * C * 4)
+
+
+def warp_tokens_bwd_bytes(B, C, H, W, s=4):
+    """Backward of the pooling half: the rows are re-staged from x and the flow, d(stack) is written once."""
+    return B * (4 * C * H * W * s + 16 * H * W + 4 * C * H * W * s + 2 * 4 * 8 * C * 4)
+
+
+class _WarpTokens(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flow, weight, bias):
+        B, C, _, H, W = x.shape
+        x = x.contiguous(memory_format=torch.channels_last_3d)
+        ctx.flow_dtype = flow.dtype
+        flow = flow.float().contiguous()
+        wa = weight.reshape(weight.shape[0], C).contiguous().float()
+        ba = bias.contiguous().float()
+        tokens = torch.empty((B, 4, 8, C), dtype=torch.float32, device=x.device)
+        stats = torch.empty((B, 4, 16), dtype=torch.float32, device=x.device)
+        xs, ys = base_grid(W, x.device), base_grid(H, x.device)
+        lib = _lib.load()
+        n = int(lib.smow_tokenizer_workspace_bytes(B, C, H * W))
+        ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device_of(x):
+            _meta(B=B, C=C, H=H, W=W)
+            _call("warp_tokens_fwd", warp_tokens_fwd_bytes(B, C, H, W), lib.smow_warp_tokenizer_fwd,
+                  x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(), wa.data_ptr(), ba.data_ptr(),
+                  tokens.data_ptr(), stats.data_ptr(), B, C, H, W, _lib.F32, _lib.NDHWC, ws.data_ptr(), n, _stream())
+        ctx.save_for_backward(x, flow, wa, ba, tokens, stats)
+        ctx.wshape = tuple(weight.shape)
+        return tokens
+
+    @staticmethod
+    def backward(ctx, gtokens):
+        x, flow, wa, ba, tokens, stats = ctx.saved_tensors
+        B, C, _, H, W = x.shape
+        gtokens = gtokens.contiguous().float()
+        gstack = _empty((B, C, 4, H, W), x, _lib.NDHWC)
+        gwa, gba = torch.empty_like(wa), torch.empty_like(ba)
+        gx = _empty(tuple(x.shape), x, _lib.NDHWC)
+        gflow = torch.empty_like(flow)
+        xs, ys = base_grid(W, x.device), base_grid(H, x.device)
+        lib = _lib.load()
+        n = int(lib.smow_tokenizer_workspace_bytes(B, C, H * W))
+        ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+        fws, fws_bytes = _bwd_workspace(lib, x, _lib.NDHWC, B, H, W)
+        with torch.cuda.device_of(x):
+            _meta(B=B, C=C, H=H, W=W)
+            _call("warp_tokens_bwd", warp_tokens_bwd_bytes(B, C, H, W), lib.smow_warp_tokenizer_bwd,
+                  gtokens.data_ptr(), x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(), wa.data_ptr(),
+                  ba.data_ptr(), tokens.data_ptr(), stats.data_ptr(), gstack.data_ptr(), gwa.data_ptr(), gba.data_ptr(),
+                  B, C, H, W, _lib.F32, _lib.NDHWC, ws.data_ptr(), n, _stream())
+            _meta(B=B, C=C, H=H, W=W, dtype=_lib.F32, layout=_lib.NDHWC, pair=0)
+            _call("warp_stack_bwd", warp_bwd_bytes(B, C, H, W, 4), lib.smow_warp_stack_bwd,
+                  gstack.data_ptr(), x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),
+                  gx.data_ptr(), gflow.data_ptr(), B, C, H, W, _lib.F32, _lib.NDHWC,
+                  fws.data_ptr() if fws is not None else None, fws_bytes, _stream())
+        return gx, gflow.to(ctx.flow_dtype), gwa.view(ctx.wshape), gba
+
+
+def warp_tokens_supported(x, weight):
+    """The fused form exists for what the two models run: fp32 (B,C,2,H,W) with C = 16 / 32, token_len = 8."""
+    return bool(x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.shape[2] == 2 and x.shape[0] > 0
+                and weight.shape[0] == 8 and _lib.load().smow_warp_tokenizer_supported(int(x.shape[1])))
+
+
+def warp_tokens(x, flow, weight, bias):
+    """``semantic_tokens(flow_warp(x, flow), weight, bias)`` in one pass over ``x``: the (B,C,4,H,W) stack that
+    ``OFW.flow_warp`` returns (reference models/SMOW_Net.py:612-638) has a single consumer, the tokenizer of
+    ``Transformer_Encoder`` (:176-187), so its rows are produced in shared memory and pooled there -> (B, 4, 8, C).
+    Backward: d(stack) is produced by the same re-staged pass and handed to the warp backward."""
+    _require_cuda(x, flow, weight, bias)
+    if x.dim() != 5 or x.shape[2] != 2:
+        raise RuntimeError("warp_tokens: input must be (B,C,2,H,W), got %s" % (tuple(x.shape),))
+    B, C, _, H, W = x.shape
+    if tuple(flow.shape) != (B, 2, 2, H, W):
+        raise RuntimeError("warp_tokens: flow must be (B,2,2,H,W)=%s, got %s" % ((B, 2, 2, H, W), tuple(flow.shape)))
+    if tuple(weight.shape[:2]) != (8, C) or bias.numel() != 8:
+        raise RuntimeError("warp_tokens: conv_a must be (8,%d,1,1) / (8,), got %s / %s" % (C, tuple(weight.shape), tuple(bias.shape)))
+    if not warp_tokens_supported(x, weight):
+        raise RuntimeError("warp_tokens: built for fp32 stacks with C = 16 / 32 (and tok_variant != 0)")
+    return _WarpTokens.apply(x, flow, weight, bias)
+
+
 # ----------------------------------------------------------------------------- N4: cyclic temporal frame mix
 def frame_mix_bytes(B, C, hw, s=4):
     """Algorithmic bytes of one apply pass: the 4-frame tensor read once and written once."""

@@ -129,6 +129,29 @@ def build(name, m, dev, gen, sigma=0.3):
                                                        tokens.data_ptr(), stats.data_ptr(), gx.data_ptr(), gwa.data_ptr(),
                                                        gba.data_ptr(), B, C, hw, _lib.F32, _lib.NDHWC, ws.data_ptr(), n, st()), name)
         return fn, ops.tokenizer_bwd_bytes(B, C, hw), ops.tokenizer_bwd_bytes(B, C, hw), (x, gx, ws, gt)
+    if name in ("warp_tokens_fwd", "warp_tokens_bwd"):
+        B, C, H, W = m["B"], m["C"], m["H"], m["W"]
+        x = _t((B, C, 2, H, W), dev, torch.float32, _lib.NDHWC, gen)
+        flow = torch.randn(B, 2, 2, H, W, device=dev, generator=gen) * sigma
+        xs, ys = ops.base_grid(W, dev), ops.base_grid(H, dev)
+        wa, ba = torch.randn(8, C, device=dev, generator=gen) / 4, torch.randn(8, device=dev, generator=gen)
+        tokens, stats = torch.empty(B, 4, 8, C, device=dev), torch.empty(B, 4, 16, device=dev)
+        n = int(lib.smow_tokenizer_workspace_bytes(B, C, H * W))
+        ws = torch.empty(max(n, 16), dtype=torch.uint8, device=dev)
+        fwd = lambda: _lib.check(lib.smow_warp_tokenizer_fwd(x.data_ptr(), flow.data_ptr(), xs.data_ptr(), ys.data_ptr(),  # noqa: E731
+                                                             wa.data_ptr(), ba.data_ptr(), tokens.data_ptr(), stats.data_ptr(),
+                                                             B, C, H, W, _lib.F32, _lib.NDHWC, ws.data_ptr(), n, st()), name)
+        if name == "warp_tokens_fwd":
+            return fwd, ops.warp_tokens_fwd_bytes(B, C, H, W), ops.warp_tokens_fwd_bytes(B, C, H, W), (x, flow, ws)
+        fwd()                                                              # tokens / stats must be the forward's outputs
+        gt = torch.randn(B, 4, 8, C, device=dev, generator=gen)
+        gstack = torch.empty((B, C, 4, H, W), device=dev).contiguous(memory_format=CL3)
+        gwa, gba = torch.empty_like(wa), torch.empty_like(ba)
+        fn = lambda: _lib.check(lib.smow_warp_tokenizer_bwd(gt.data_ptr(), x.data_ptr(), flow.data_ptr(), xs.data_ptr(),  # noqa: E731
+                                                            ys.data_ptr(), wa.data_ptr(), ba.data_ptr(), tokens.data_ptr(),
+                                                            stats.data_ptr(), gstack.data_ptr(), gwa.data_ptr(), gba.data_ptr(),
+                                                            B, C, H, W, _lib.F32, _lib.NDHWC, ws.data_ptr(), n, st()), name)
+        return fn, ops.warp_tokens_bwd_bytes(B, C, H, W), ops.warp_tokens_bwd_bytes(B, C, H, W), (x, flow, gstack, ws, gt)
     if name in ("frame_mix_fwd", "frame_mix_bwd", "frame_mix_wgrad"):
         B, C, T, hw, tc = m["B"], m["C"], m["T"], m["hw"], m.get("tc", 1)
         x = _t((B, C, T, hw, 1), dev, torch.float32, _lib.NDHWC, gen)

@@ -74,6 +74,9 @@ def use_oracle_ops(monkeypatch):
     from smow_net_b200.models import blocks
     monkeypatch.setattr(ops, "semantic_tokens", torch_ref.ref_semantic_tokens)
     monkeypatch.setattr(ops, "flow_head", torch_ref.ref_flow_head)            # row N1
+    # rows A1 + N2 fused: the reference's own sequence, flow_warp then the pooling
+    monkeypatch.setattr(ops, "warp_tokens",
+                        lambda x, flow, w, b: torch_ref.ref_semantic_tokens(torch_ref.ref_flow_warp(x, flow), w, b))
 
     def mix(frames5d, shared, own, shift=1, own_off=1):
         T, bias = len(own), None

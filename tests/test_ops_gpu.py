@@ -472,6 +472,70 @@ def test_semantic_tokens_sharp_attention_and_errors():
         ops.semantic_tokens(x[:, :12], weight[:, :12], bias)      # C/4 = 3 is not a power of two
 
 
+# ------------------------------------------------------------------------------------- rows A1 + N2 fused: warp -> tokens
+@pytest.mark.parametrize("case", [(2, 16, 128, 128, 0.7, 1.0), (2, 32, 128, 128, 0.3, 0.5), (1, 16, 24, 40, 8.0, 1.0),
+                                  (3, 32, 9, 12, 2.0, 1.0), (1, 16, 33, 65, 0.0, 2.0), (1, 32, 64, 96, 8.0, 1.0)])
+def test_warp_tokens_equals_tokenizer_of_the_warped_stack(case):
+    """ops.warp_tokens (the stack is produced in shared memory, never in HBM) against the reference's sequence
+    OFW.flow_warp -> Transformer_Encoder pooling (models/SMOW_Net.py:612-638 -> :176-187) through the oracle, forward and
+    backward (d x, d flow, d conv_a), and bit for bit against the two-launch CUDA path it replaces.  Shapes cover ragged
+    chunks (H*W not a multiple of 512), non-power-of-two widths, zero flow and border-clamped sigma = 8 flows."""
+    B, C, H, W, sigma, wscale = case
+    g = torch.Generator(device=DEV).manual_seed(7 * B + C + H * W)
+    x = torch.randn(B, C, 2, H, W, device=DEV, generator=g).contiguous(memory_format=CL3)
+    flow = torch.randn(B, 2, 2, H, W, device=DEV, generator=g) * sigma
+    weight = torch.randn(8, C, 1, 1, device=DEV, generator=g) * wscale / C ** 0.5
+    bias = torch.randn(8, device=DEV, generator=g)
+    gt = torch.randn(B, 4, 8, C, device=DEV, generator=g)
+    assert ops.warp_tokens_supported(x, weight)
+    leaves = [t.clone().requires_grad_(True) for t in (x, flow, weight, bias)]
+    before = _lib.launch_count()
+    tok = ops.warp_tokens(*leaves)
+    assert _lib.launch_count() - before == 2                        # chunk kernel + combine: no warp launch, no stack
+    tok.backward(gt)
+    # (1) the oracle: the reference's own op sequence on the same device — the warp in fp32 (its coordinate chain is an
+    # fp32 contract), the pooling evaluated in fp64 like the stand-alone tokenizer test
+    ref_leaves = [x.clone().requires_grad_(True), flow.clone().requires_grad_(True),
+                  weight.double().requires_grad_(True), bias.double().requires_grad_(True)]
+    ref = _ref_tokens(torch_ref.ref_flow_warp(ref_leaves[0], ref_leaves[1]).double(), *ref_leaves[2:])
+    ref.backward(gt.double())
+    assert float((tok.detach() - ref.detach()).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+    for name, a, b in zip(("gx", "gflow", "gweight", "gbias"), leaves, ref_leaves):
+        err = float((a.grad.double() - b.grad.double()).abs().max())
+        assert err <= 2e-5 * max(1.0, float(b.grad.abs().max())), (name, err)
+    # (2) the two-launch CUDA path: the staged rows are the warp kernel's output bit for bit, so everything is identical
+    two = [t.clone().requires_grad_(True) for t in (x, flow, weight, bias)]
+    tok2 = ops.semantic_tokens(ops.flow_warp(two[0], two[1], (H, W)), two[2], two[3])
+    tok2.backward(gt)
+    assert torch.equal(tok2, tok)
+    for name, a, b in zip(("gx", "gflow", "gweight", "gbias"), leaves, two):
+        if name == "gx" and sigma >= 0.7:       # taps farther than a pixel are added by the far pass with L2 reductions: order-free
+            assert float((a.grad - b.grad).abs().max()) <= 1e-5 * max(1.0, float(b.grad.abs().max())), name
+        else:
+            assert torch.equal(a.grad, b.grad), name
+    assert leaves[0].grad.is_contiguous(memory_format=CL3)
+
+
+def test_warp_tokens_argument_errors_and_unsupported_channels():
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(1, 16, 2, 16, 16, device=DEV, generator=g).contiguous(memory_format=CL3)
+    flow = torch.zeros(1, 2, 2, 16, 16, device=DEV)
+    w, b = torch.randn(8, 16, 1, 1, device=DEV, generator=g), torch.zeros(8, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.warp_tokens(x.cpu(), flow.cpu(), w.cpu(), b.cpu())              # no CPU path
+    with pytest.raises(RuntimeError):
+        ops.warp_tokens(x, flow[:, :, :, :8], w, b)                          # flow of another size
+    with pytest.raises(RuntimeError):
+        ops.warp_tokens(x, flow, w[:, :8], b)                                # conv_a of another width
+    x64 = torch.randn(1, 64, 2, 16, 16, device=DEV, generator=g).contiguous(memory_format=CL3)
+    assert not ops.warp_tokens_supported(x64, torch.randn(8, 64, 1, 1, device=DEV))     # the modules then run two launches
+    assert not ops.warp_tokens_supported(x.bfloat16(), w)
+    # zero flow: frames 1 / 2 resample frames 0 / 3 at their own pixel centres (up to the rounding of the base grid)
+    tok = ops.warp_tokens(x, flow, w, b)
+    d01, d23 = float((tok[:, 0] - tok[:, 1]).abs().max()), float((tok[:, 2] - tok[:, 3]).abs().max())
+    assert d01 <= 1e-4 and d23 <= 1e-4, (d01, d23)
+
+
 @pytest.mark.parametrize("case", [(2, 16, 128, 128, 0.7), (1, 32, 64, 96, 3.0), (1, 128, 9, 33, 1.0), (2, 4, 31, 17, 5.0)])
 def test_warp_ndhwc_forward_kernels_agree_bit_for_bit(case, variants):
     """The default NDHWC forward (one coordinate chain per pixel, footprints passed by warp shuffles) and the plain
