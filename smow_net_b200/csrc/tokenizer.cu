@@ -488,7 +488,8 @@ static int warp_tok_geom(TokGeom& g, TokWarpSrc& src, const void* x, const float
   if (!flow || !xs || !ys) return fail(SMOW_EINVAL, "warp_tokenizer: null pointer");
   if (!tok_use_mma(C))
     return fail(SMOW_EDTYPE, "warp_tokenizer: built on the tensor-core tokenizer kernels (C = 16 / 32, tok_variant != 0)");
-  if ((int64_t)B * 4 * H * W * C >= ((int64_t)1 << 31)) return fail(SMOW_ERANGE, "warp_tokenizer: tensor too large for 32-bit tile indexing");
+  if ((int64_t)B * 4 * H * W * C >= ((int64_t)1 << 31) || (int64_t)H * W >= ((int64_t)1 << 29))
+    return fail(SMOW_ERANGE, "warp_tokenizer: tensor too large for 32-bit tile indexing");
   src.x = (const float*)x; src.flow = flow; src.xs = xs; src.ys = ys; src.H = H; src.W = W; src.wshift = -1;
   for (int s = 0; s < 31; ++s) if ((1 << s) == W) src.wshift = s;
   return 0;

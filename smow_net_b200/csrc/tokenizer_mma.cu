@@ -81,10 +81,13 @@ __device__ __forceinline__ void stage_warped_rows(float* __restrict__ rows, cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HW = s.H * s.W, W = s.W;
   const int v = lane & (Q - 1), sub = lane >> QSHIFT;
-  const float* src = s.x + (int64_t)(b * 2 + t) * HW * C + v * 4;
+  const float* src = s.x + (int64_t)(b * 2 + t) * HW * C;      // CTA-uniform base + 32-bit element offsets below
   const float* fl = s.flow + ((int64_t)(b * 2) * 2 + t) * HW;
-  // the warp's GPW groups are independent: all flow loads first, then the chains, then the gathers of one group at a time
-  // (16 / 32 independent 16-byte loads in flight per thread) — the staging is latency bound, not bandwidth bound
+  // The staging is bound by instruction issue and load latency, not by bandwidth, so it is written for few instructions and
+  // many independent loads: the warp's GPW groups are independent (all flow loads first, then the chains, then the gathers);
+  // a tap outside the image gets weight 0 and is re-pointed at the nw tap (always in bounds), which leaves the sum bit for
+  // bit what ATen's skipped tap gives (r + c * 0 = r) with four unconditional loads and a flat FMA chain; a dead pixel (ragged
+  // chunk) gets four zero weights.  Per pixel one packed word (nw offset, x / y step present) and four weights are shuffled.
   float fx[GPW], fy[GPW];
 #pragma unroll
   for (int k = 0; k < GPW; ++k) {
@@ -93,19 +96,22 @@ __device__ __forceinline__ void stage_warped_rows(float* __restrict__ rows, cons
     fx[k] = live ? __ldg(fl + p0 + pl) : 0.f;
     fy[k] = live ? __ldg(fl + p0 + pl + 2 * (int64_t)HW) : 0.f;
   }
-  int own_o[GPW], own_flags[GPW];
+  int own_o[GPW];
   float own_nw[GPW], own_ne[GPW], own_sw[GPW], own_se[GPW];
 #pragma unroll
   for (int k = 0; k < GPW; ++k) {
     const int pl = (warp * GPW + k) * 32 + lane;
-    const int p = pl < n ? p0 + pl : p0;                        // dead lanes: any valid pixel (their rows are zeroed below)
+    const bool live = pl < n;
+    const int p = live ? p0 + pl : p0;
     const int h = s.wshift >= 0 ? (p >> s.wshift) : (p / W), w = p - h * W;
     const Footprint fp = footprint_auto(__ldg(s.xs + w), __ldg(s.ys + h), fx[k], fy[k], W, s.H);
-    own_nw[k] = __fmul_rn(fp.wx0, fp.wy0); own_ne[k] = __fmul_rn(fp.wx1, fp.wy0);
-    own_sw[k] = __fmul_rn(fp.wx0, fp.wy1); own_se[k] = __fmul_rn(fp.wx1, fp.wy1);
-    own_o[k] = fp.y0 * W + fp.x0;
-    own_flags[k] = (fp.x1ok ? 1 : 0) | (fp.y1ok ? 2 : 0);
+    own_nw[k] = live ? __fmul_rn(fp.wx0, fp.wy0) : 0.f;
+    own_ne[k] = live && fp.x1ok ? __fmul_rn(fp.wx1, fp.wy0) : 0.f;
+    own_sw[k] = live && fp.y1ok ? __fmul_rn(fp.wx0, fp.wy1) : 0.f;
+    own_se[k] = live && fp.x1ok && fp.y1ok ? __fmul_rn(fp.wx1, fp.wy1) : 0.f;
+    own_o[k] = ((fp.y0 * W + fp.x0) << 2) | (fp.x1ok ? 1 : 0) | (fp.y1ok ? 2 : 0);     // HW < 2^29 (checked by the host)
   }
+  const int rowC = W * C;
 #pragma unroll
   for (int k = 0; k < GPW; ++k) {
     const int g0 = (warp * GPW + k) * 32;
@@ -113,25 +119,20 @@ __device__ __forceinline__ void stage_warped_rows(float* __restrict__ rows, cons
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
       const int sl = j * PPW + sub;                               // lane that holds this pixel's footprint
-      const int o_nw = __shfl_sync(0xffffffffu, own_o[k], sl), flags = __shfl_sync(0xffffffffu, own_flags[k], sl);
+      const int o = __shfl_sync(0xffffffffu, own_o[k], sl);
       const float nw = __shfl_sync(0xffffffffu, own_nw[k], sl), ne = __shfl_sync(0xffffffffu, own_ne[k], sl);
       const float sw = __shfl_sync(0xffffffffu, own_sw[k], sl), se = __shfl_sync(0xffffffffu, own_se[k], sl);
-      r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g0 + sl < n) {
-        const float* tp = src + (int64_t)o_nw * C;
-        // taps outside the image are re-pointed at the nw tap (always in bounds) and dropped from the sum: four
-        // unconditional loads in flight instead of three dependent branches
-        const float4 a = __ldg(reinterpret_cast<const float4*>(tp));
-        const float4 c1 = __ldg(reinterpret_cast<const float4*>(tp + ((flags & 1) ? C : 0)));
-        const float4 c2 = __ldg(reinterpret_cast<const float4*>(tp + ((flags & 2) ? (int64_t)W * C : 0)));
-        const float4 c3 = __ldg(reinterpret_cast<const float4*>(tp + (flags == 3 ? (int64_t)(W + 1) * C : 0)));
-        float4 q;
-        q.x = __fmul_rn(a.x, nw); q.y = __fmul_rn(a.y, nw); q.z = __fmul_rn(a.z, nw); q.w = __fmul_rn(a.w, nw);
-        if (flags & 1) { q.x = fmaf(c1.x, ne, q.x); q.y = fmaf(c1.y, ne, q.y); q.z = fmaf(c1.z, ne, q.z); q.w = fmaf(c1.w, ne, q.w); }
-        if (flags & 2) { q.x = fmaf(c2.x, sw, q.x); q.y = fmaf(c2.y, sw, q.y); q.z = fmaf(c2.z, sw, q.z); q.w = fmaf(c2.w, sw, q.w); }
-        if (flags == 3) { q.x = fmaf(c3.x, se, q.x); q.y = fmaf(c3.y, se, q.y); q.z = fmaf(c3.z, se, q.z); q.w = fmaf(c3.w, se, q.w); }
-        r[j] = q;
-      }
+      const uint32_t o0 = (uint32_t)(o >> 2) * C + v * 4, dx = (o & 1) ? C : 0, dy = (o & 2) ? rowC : 0;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + o0));
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(src + o0 + dx));
+      const float4 c2 = __ldg(reinterpret_cast<const float4*>(src + o0 + dy));
+      const float4 c3 = __ldg(reinterpret_cast<const float4*>(src + o0 + dx + dy));
+      float4 q;                                                   // ATen's order: nw, ne, sw, se
+      q.x = __fmul_rn(a.x, nw); q.y = __fmul_rn(a.y, nw); q.z = __fmul_rn(a.z, nw); q.w = __fmul_rn(a.w, nw);
+      q.x = fmaf(c1.x, ne, q.x); q.y = fmaf(c1.y, ne, q.y); q.z = fmaf(c1.z, ne, q.z); q.w = fmaf(c1.w, ne, q.w);
+      q.x = fmaf(c2.x, sw, q.x); q.y = fmaf(c2.y, sw, q.y); q.z = fmaf(c2.z, sw, q.z); q.w = fmaf(c2.w, sw, q.w);
+      q.x = fmaf(c3.x, se, q.x); q.y = fmaf(c3.y, se, q.y); q.z = fmaf(c3.z, se, q.z); q.w = fmaf(c3.w, se, q.w);
+      r[j] = g0 + sl < n ? q : make_float4(0.f, 0.f, 0.f, 0.f);   // dead rows are exact zeros whatever x holds
     }
 #pragma unroll
     for (int j = 0; j < Q; ++j) *reinterpret_cast<float4*>(rows + (g0 + j * PPW + sub) * C + v * 4) = r[j];
@@ -146,6 +147,8 @@ __device__ __forceinline__ bool stage_chunk(float* rows, uint64_t* bar, const fl
                                             int bk, int p0, int n, int64_t hw) {
   const int f = bk & 3;
   const bool warped = FUSED && (f == 1 || f == 2);
+  // the warp staging comes first: every thread is still converged here, so its shuffles need no re-convergence code
+  if (warped) stage_warped_rows<C, CHUNK, NT>(rows, s, bk >> 2, f - 1, p0, n);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
@@ -156,8 +159,7 @@ __device__ __forceinline__ bool stage_chunk(float* rows, uint64_t* bar, const fl
       bulk_g2s(rows, from, (uint32_t)n * C * 4u, bar);
     }
   }
-  if (warped) stage_warped_rows<C, CHUNK, NT>(rows, s, bk >> 2, f - 1, p0, n);
-  else if (n < CHUNK) zero_dead_rows(rows, n, CHUNK, C, NT);
+  if (!warped && n < CHUNK) zero_dead_rows(rows, n, CHUNK, C, NT);
   return !warped;
 }
 
