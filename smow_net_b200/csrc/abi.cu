@@ -24,6 +24,7 @@ static Knob g_knobs[OPT_COUNT] = {
     {"ndhwc_bwd_pf", {-1}},      // NDHWC tile gather: next item's x taps prefetched into shared-memory slots (-1 = auto: C >= 128, 0 = off, 1 = on)
     {"tc_debug", {0}},           // bring-up switches of the tcgen05 kernels (0 in production)
     {"tok_variant", {-1}},       // tokenizer: -1 = auto (tensor-core MMA kernels for C = 16 / 32), 0 = FP32-pipe kernels
+    {"bn_bwd_rows", {1}},        // fused BatchNorm + lerp backward: 1 = row-wise kernel (every gradient line fetched once), 0 = split dec / skip CTAs
 };
 
 int fail(int code, const char* fmt, ...) {

@@ -13,7 +13,7 @@ int  fail(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 int  option(int id);
 enum OptionId { OPT_WARP_FWD_VARIANT = 0, OPT_WARP_BWD_VARIANT, OPT_TLERP_VARIANT,
-                OPT_BWD_ROWS, OPT_BWD_HALO, OPT_FWD_ROWS, OPT_FWD_HALO, OPT_CVEC_PF, OPT_BWD_CHUNK_MB, OPT_NDHWC_BWD_ROWS, OPT_NDHWC_BWD_PF, OPT_TC_DEBUG, OPT_TOK_VARIANT, OPT_COUNT };
+                OPT_BWD_ROWS, OPT_BWD_HALO, OPT_FWD_ROWS, OPT_FWD_HALO, OPT_CVEC_PF, OPT_BWD_CHUNK_MB, OPT_NDHWC_BWD_ROWS, OPT_NDHWC_BWD_PF, OPT_TC_DEBUG, OPT_TOK_VARIANT, OPT_BN_BWD_ROWS, OPT_COUNT };
 
 struct DeviceInfo { int sms; int smem_optin; };
 DeviceInfo device_info();   // cached per device (abi.cu)

@@ -5,6 +5,7 @@
 // align_corners=True) then torch.cat([dec, x_up], dim=1).  With unchanged h,w the 8-tap
 // trilinear kernel degenerates to out[t] = (1-l_t) T1 + l_t T2, l = {0, 1/3, 2/3, 1} in
 // fp32 (ATen UpSampleTrilinear3d: rdepth = (2-1)/(4-1); frames 0 and 3 are exact copies).
+#include <type_traits>
 #include "common.cuh"
 
 namespace smow {
@@ -392,6 +393,75 @@ act_tlerp_cat_bwd_ndhwc_kernel(const T* __restrict__ gcat, const T* __restrict__
   }
 }
 
+// Row-wise form of the BatchNorm + LeakyReLU + lerp backward (fp32, training — the form the models run).  ncu on the kernel
+// above at LW's largest level (28 + 16 channels: 176-byte gradient rows): 478 MB read from HBM for 302 MB of operands, and
+// the same whenever the decoder / skip boundary falls inside a 128-byte line (24 + 8 channels: 337 MB for 235 MB; 32 + 32:
+// exact).  The decoder slice and the skip slice of a gradient row are read by different CTAs — or, in a first row-wise
+// attempt, by different warps of one CTA whose loops drift apart — so by the time the second reader arrives the line has
+// left the L2 (the gradient alone is larger than the cache) and comes from HBM again.
+// Here ONE load instruction reads the whole row: thread = (pixel, 16-byte vector v of the concat row), 256 / q pixels per
+// CTA iteration (q = (Cd + Cs) / 4); every thread loads its vector for the four frames (fully contiguous rows across the
+// lanes), then lanes v < Cd / 4 do the BatchNorm + LeakyReLU backward of their vector (y loaded through L1, parameters in
+// registers, 4 frames = 8 independent loads in flight) and the others the lerp backward (four frames in, two out).  Every
+// gradient line is requested once.  Pixels are walked from the END (see above).
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__global__ void __launch_bounds__(256, 3)
+bn_act_tlerp_cat_bwd_rows_kernel(const float* __restrict__ gcat, const float* __restrict__ y, float* __restrict__ gy,
+                                 float* __restrict__ g1, float* __restrict__ g2, int64_t sB, int Cd, int Cs, int64_t hw,
+                                 int64_t npix, FastDiv fhw, float slope, const float* __restrict__ bn) {
+  const int qd = Cd >> 2, q = (Cd + Cs) >> 2, ppi = 256 / q;
+  const int pl = threadIdx.x / q, v = threadIdx.x - pl * q;
+  if (pl >= ppi) return;
+  const int Ct = Cd + Cs;
+  const bool is_dec = v < qd;
+  const int64_t fs = hw * Ct, fd = hw * Cd, step = (int64_t)gridDim.x * ppi;
+  const bool small = npix < (1ll << 31);
+  const int vp = is_dec ? v : 0;                                  // skip lanes load (and ignore) vector 0's parameters
+  const float4 sc = ldg4(bn + 4 * vp), sh = ldg4(bn + Cd + 4 * vp), mu = ldg4(bn + 2 * Cd + 4 * vp);
+  const float4 is = ldg4(bn + 3 * Cd + 4 * vp), k1 = ldg4(bn + 4 * Cd + 4 * vp), k2 = ldg4(bn + 5 * Cd + 4 * vp);
+  const LerpW lw = lerp_weights();
+  for (int64_t i0 = (int64_t)blockIdx.x * ppi + pl; i0 < npix; i0 += step) {
+    const int64_t i = npix - 1 - i0;
+    int64_t b, p;
+    if (small) { uint32_t ub, up; fast_split((uint32_t)i, fhw, ub, up); b = ub; p = up; }
+    else { b = i / hw; p = i - b * hw; }
+    const int64_t r0 = b * 4 * hw + p;
+    const float* g = gcat + r0 * Ct + v * 4;
+    float4 gv[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) gv[f] = __ldcs(reinterpret_cast<const float4*>(g + f * fs));
+    if (is_dec) {
+      const float* yy = y + r0 * Cd + v * 4;
+      float4 yv[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) yv[f] = ldg4(yy + f * fd);
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        float4 o;
+#define SMOW_BN_BWD(c)                                                                   \
+  {                                                                                      \
+    const float u = fmaf(yv[f].c, sc.c, sh.c), du = u > 0.f ? gv[f].c : gv[f].c * slope; \
+    const float xh = (yv[f].c - mu.c) * is.c;                                            \
+    o.c = sc.c * (du - k1.c - xh * k2.c);                                                \
+  }
+        SMOW_BN_BWD(x) SMOW_BN_BWD(y) SMOW_BN_BWD(z) SMOW_BN_BWD(w)
+#undef SMOW_BN_BWD
+        *reinterpret_cast<float4*>(gy + (r0 + f * hw) * Cd + v * 4) = o;
+      }
+    } else {
+      float4 r1, r2;
+#define SMOW_LERP_BWD(c)                                                  \
+  r1.c = fmaf(lw.a2, gv[2].c, fmaf(lw.a1, gv[1].c, gv[0].c));             \
+  r2.c = __fadd_rn(fmaf(lw.b2, gv[2].c, __fmul_rn(lw.b1, gv[1].c)), gv[3].c);
+      SMOW_LERP_BWD(x) SMOW_LERP_BWD(y) SMOW_LERP_BWD(z) SMOW_LERP_BWD(w)
+#undef SMOW_LERP_BWD
+      const int64_t o = b * sB + p * Cs + (v - qd) * 4;
+      *reinterpret_cast<float4*>(g1 + o) = r1;
+      *reinterpret_cast<float4*>(g2 + o) = r2;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------
 // host dispatch
 // ------------------------------------------------------------------------------
@@ -459,6 +529,18 @@ static int act_bwd_ndhwc(const T* gcat, const T* z, T* gz, T* g1, T* g2, int64_t
   if (Cd <= 0 || Cd % V || Cs % V || !aligned16(gcat) || !aligned16(z) || !aligned16(gz) ||
       (Cs > 0 && (!aligned16(g1) || !aligned16(g2) || sB % V)))
     return fail(SMOW_EALIGN, "act_tlerp_cat NDHWC needs Cd > 0, Cd and Cs multiples of %d and 16 B aligned tensors", V);
+  if constexpr (std::is_same<T, float>::value) {
+    const int q = (Cd + Cs) / 4;
+    if (bn != nullptr && q <= 128 && option(OPT_BN_BWD_ROWS) != 0) {      // training form: whole concat rows per CTA
+      const int ppi = 256 / q;
+      const int64_t npix = (int64_t)B * hw, want = (npix + ppi - 1) / ppi;
+      const int cap8 = device_info().sms * 3;                             // 3 resident CTAs per SM: one wave, static pixel split
+      bn_act_tlerp_cat_bwd_rows_kernel<<<(int)(want < cap8 ? want : cap8), 256, 0, st>>>(gcat, z, gz, g1, g2, sB, Cd, Cs, hw, npix,
+                                                                                         make_fastdiv(hw), slope, bn);
+      count_launch();
+      return check_launch("bn_act_tlerp_cat_bwd (rows)");
+    }
+  }
   const int64_t n_dec = (int64_t)B * 4 * hw * (Cd / V), n_skip = (int64_t)B * hw * (Cs / V);
   const int cap = device_info().sms * 8;
   const int nb_dec = (int)((n_dec + 255) / 256 < cap ? (n_dec + 255) / 256 : cap);
