@@ -25,6 +25,12 @@ CASES = [
     ("tlerp_cat_bwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 1}),
     ("tlerp_cat_fwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 2}),
     ("tlerp_cat_bwd", {"B": B, "Cd": 32, "Cs": 32, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 2}),
+    ("tlerp_cat_fwd", {"B": 16, "Cd": 28, "Cs": 16, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 2}),
+    ("tlerp_cat_bwd", {"B": 16, "Cd": 28, "Cs": 16, "hw": H * H, "dtype": F32, "layout": ND, "pair": 0, "act": 2}),
+    ("warp_tokens_fwd", {"B": B, "C": C, "H": H, "W": H}),
+    ("warp_tokens_bwd", {"B": B, "C": C, "H": H, "W": H}),
+    ("warp_tokens_fwd", {"B": B, "C": 16, "H": H, "W": H}),
+    ("warp_tokens_bwd", {"B": B, "C": 16, "H": H, "W": H}),
     ("tokenizer_fwd", {"B": B, "C": C, "hw": H * H}),
     ("tokenizer_bwd", {"B": B, "C": C, "hw": H * H}),
     ("tokenizer_fwd", {"B": B, "C": 16, "hw": H * H}),
