@@ -180,9 +180,10 @@ tok_fwd_mma_kernel(const float* __restrict__ x, const TokWarpSrc src, const floa
   float* mw = tw + NW * TOK_L * C;                        // [NW][8]
   float* sw = mw + NW * TOK_L;                            // [NW][8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  // fused form: the CTAs that warp (frames 1, 2) are the long ones and are dispatched first (frame order 1, 2, 3, 0)
-  const int nb = gridDim.y >> 2;
-  const int bk = FUSED ? 4 * (int)(blockIdx.y % nb) + (((int)(blockIdx.y / nb) + 1) & 3) : (int)blockIdx.y;
+  // fused form: frame order 1, 0, 2, 3 within a pair — the CTAs that warp input frame t and the ones that copy it run back
+  // to back, so the second reader finds the frame in the L2 (ncu, B = 64, C = 32, dispatched "all warps first": 544 MB read
+  // from HBM for a 268 MB x)
+  const int bk = FUSED ? (int)(blockIdx.y & ~3u) + ((0x3201 >> (4 * (blockIdx.y & 3))) & 3) : (int)blockIdx.y;
   const int p0 = blockIdx.x * CHUNK;
   const int n = (int64_t)p0 + CHUNK < geo.hw ? CHUNK : (int)(geo.hw - p0);
   const bool copied = stage_chunk<C, CHUNK, NT, FUSED>(dyn, &bar, x, src, bk, p0, n, geo.hw);
@@ -294,9 +295,10 @@ tok_bwd_mma_kernel(const float* __restrict__ gtok, const float* __restrict__ x, 
   float* dww = dyn + CHUNK * C + (C / 8) * 2 * 32 * 4;    // [NW][8][C]
   float* dbw = dww + NW * TOK_L * C;                      // [NW][8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  // fused form: the CTAs that warp (frames 1, 2) are the long ones and are dispatched first (frame order 1, 2, 3, 0)
-  const int nb = gridDim.y >> 2;
-  const int bk = FUSED ? 4 * (int)(blockIdx.y % nb) + (((int)(blockIdx.y / nb) + 1) & 3) : (int)blockIdx.y;
+  // fused form: frame order 1, 0, 2, 3 within a pair — the CTAs that warp input frame t and the ones that copy it run back
+  // to back, so the second reader finds the frame in the L2 (ncu, B = 64, C = 32, dispatched "all warps first": 544 MB read
+  // from HBM for a 268 MB x)
+  const int bk = FUSED ? (int)(blockIdx.y & ~3u) + ((0x3201 >> (4 * (blockIdx.y & 3))) & 3) : (int)blockIdx.y;
   const int p0 = blockIdx.x * CHUNK;
   const int n = (int64_t)p0 + CHUNK < geo.hw ? CHUNK : (int)(geo.hw - p0);
   const bool copied = stage_chunk<C, CHUNK, NT, FUSED>(dyn, &bar, x, src, bk, p0, n, geo.hw);
