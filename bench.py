@@ -397,9 +397,12 @@ def gpu_reference_block(args, device):
         return {"unavailable": "oracle/_ref/reference.zip absent (build it with `python -m oracle.build_ref` where /root/reference exists)"}
     lw = ref_runtime.time_gpu_fwd_bwd("lw", args.batch, steps=max(3, min(args.steps, 10)), warmup=3, device=device)
     s16 = ref_runtime.time_gpu_fwd_bwd("s", 16, steps=5, warmup=2, device=device, train_step=True)
+    inf = ref_runtime.time_gpu_infer("s", 32, passes=4, warmup=2, device=device)      # cfg4's batches: 2 tiles = 32 crops
     return {"kind": "reference", "how": "unmodified reference modules from oracle/_ref/reference.zip, .cuda(), eager, NCDHW, CUDA events",
             "cfg2_lw_fwd_bwd": {"value": lw["pairs_per_s"], "unit": UNIT, "ms_per_step": lw["ms_per_step"], "batch": lw["batch"]},
-            "cfg3_like_s_train_step_batch16": {"value": s16["pairs_per_s"], "unit": UNIT, "ms_per_step": s16["ms_per_step"], "batch": 16}}
+            "cfg3_like_s_train_step_batch16": {"value": s16["pairs_per_s"], "unit": UNIT, "ms_per_step": s16["ms_per_step"], "batch": 16},
+            "cfg4_like_s_inference_32_crops": {"value": inf["pairs_per_s"], "unit": UNIT, "ms_per_pass": inf["ms_per_pass"],
+                                               "crops": inf["crops"], "note": "device-resident crops, no H2D (cfg4's own number includes the H2D of its host tiles)"}}
 
 
 def main():

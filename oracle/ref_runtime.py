@@ -127,3 +127,30 @@ def time_gpu_fwd_bwd(kind, batch, steps, warmup, device, train_step=False):
     del model, opt
     torch.cuda.empty_cache()
     return {"pairs_per_s": batch * steps / (ms * 1e-3), "ms_per_step": ms / steps, "batch": batch, "steps": steps}
+
+
+def time_gpu_infer(kind, crops, passes, warmup, device):
+    """The reference's inference the way test.py:124-134 runs it on the same GPU: model.cuda().eval(), no_grad, eager, NCDHW,
+    batches of `crops` 256x256 crops (one 1024x1024 tile = 16 crops), threshold 0.5.  CUDA events."""
+    import torch
+    from smow_net_b200.runtime import synthetic
+    model = build_model(kind, device).eval()
+    a, b, _ = synthetic.make_batch(crops, device=device)
+
+    def one():
+        with torch.no_grad():
+            return (model(a, b) > 0.5).sum()
+
+    for _ in range(max(1, warmup)):
+        one()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(passes):
+        one()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    del model
+    torch.cuda.empty_cache()
+    return {"pairs_per_s": crops * passes / (ms * 1e-3), "ms_per_pass": ms / passes, "crops": crops, "passes": passes}
