@@ -687,7 +687,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 warp_bwd_ndhwc_tile_bf16_kernel(const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16* __restrict__ x1,
                                 const __nv_bfloat16* __restrict__ x2, int64_t sB, const float* __restrict__ flow,
                                 const float* __restrict__ xs, const float* __restrict__ ys, __nv_bfloat16* __restrict__ gx1,
@@ -1048,7 +1048,9 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
     if ((int64_t)HW * C >= (1ll << 31)) return fail(SMOW_ERANGE, "plane too large");
     const int lshift = qs < 3 ? qs : 3;
     int R = option(OPT_NDHWC_BWD_ROWS);
-    if (R <= 0) R = lshift == 3 ? 8 : 12;
+    // measured on B200 (benchmarks/bwd_bf16_probe.py) with 4 CTAs per SM (64 registers, r2: 104 registers / 2 CTAs gave 0.30-0.34
+    // of the roofline, now 0.43-0.45): 6-row tiles for >= 64 channels, 8 rows at 32, 12 at 16
+    if (R <= 0) R = lshift == 3 ? 6 : lshift == 2 ? 8 : 12;
     if (R > H) R = H;
     const size_t smem = tile_smem_bytes(R, 1 << lshift);
     if (smem > 72 * 1024) return fail(SMOW_ERANGE, "NDHWC bf16 warp backward: tile does not fit shared memory");
