@@ -281,7 +281,7 @@ tok_fwd_mma_kernel(const float* __restrict__ x, const TokWarpSrc src, const floa
 // ---- backward ----------------------------------------------------------------------------------------------------------
 // grid (nchunks, 4*B), 4 warps; warp w owns pixels [w*PW, (w+1)*PW), 16 per iteration (two 8-pixel groups A, B).
 template <int C, int CHUNK, bool FUSED>
-__global__ void __launch_bounds__(TOKM_BWD_THREADS, 4)
+__global__ void __launch_bounds__(TOKM_BWD_THREADS, C == 16 ? 5 : 3)
 tok_bwd_mma_kernel(const float* __restrict__ gtok, const float* __restrict__ x, const TokWarpSrc src,
                    const float* __restrict__ wa,
                    const float* __restrict__ ba, const float* __restrict__ tokens, const float* __restrict__ stats,
