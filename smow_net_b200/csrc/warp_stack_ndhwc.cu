@@ -137,7 +137,9 @@ warp_fwd_ndhwc_shfl_kernel(const T* __restrict__ x1, const T* __restrict__ x2, i
     }
   }
   // ---- q steps: lanes = (32/q pixels) x (q channel vectors) ----
-  const int v = lane & (q - 1), sub = lane >> qshift, ppw = 32 >> qshift;
+  // More than 32 vectors per pixel (fp32 C = 256 / 512): blockIdx.z walks groups of 32 vectors, q = 32 per group (the chain
+  // is then run once per group: ~100 instructions per 32 pixels next to 32 x 32 gathers)
+  const int v = (lane & (q - 1)) + 32 * blockIdx.z, sub = lane >> qshift, ppw = 32 >> qshift;
   const T* src = (t ? x2 : x1) + b * sB + v * V;
   T* ob = out + (int64_t)b * 4 * HW * C + v * V;
   const int64_t slotC = (int64_t)HW * C;
@@ -1060,9 +1062,10 @@ int warp_fwd_ndhwc(const T* x1, const T* x2, int64_t sB, const float* flow, cons
   const int q = C / V;
   if ((int64_t)H * W * q >= (1ll << 31)) return fail(SMOW_ERANGE, "plane too large");
   const int qs = ilog2_exact(q);
-  if (qs >= 0 && q <= 32 && option(OPT_WARP_FWD_VARIANT) != 0) {          // default: per-pixel coordinates, shuffled
-    dim3 grid((unsigned)(((int64_t)H * W + 255) / 256), 2 * B);
-    warp_fwd_ndhwc_shfl_kernel<T><<<grid, 256, 0, st>>>(x1, x2, sB, flow, xs, ys, out, C, H, W, q, qs, ilog2_exact(W));
+  if (qs >= 0 && q <= 2048 && option(OPT_WARP_FWD_VARIANT) != 0) {        // default: per-pixel coordinates, shuffled
+    const int qg = q <= 32 ? q : 32;                                        // vectors per pixel handled by one warp pass
+    dim3 grid((unsigned)(((int64_t)H * W + 255) / 256), 2 * B, q / qg);
+    warp_fwd_ndhwc_shfl_kernel<T><<<grid, 256, 0, st>>>(x1, x2, sB, flow, xs, ys, out, C, H, W, qg, ilog2_exact(qg), ilog2_exact(W));
   } else {                                                                 // any q; also warp_fwd_variant = 0
     dim3 grid((unsigned)(((int64_t)H * W * q + 255) / 256), 2 * B);
     warp_fwd_ndhwc_kernel<T><<<grid, 256, 0, st>>>(x1, x2, sB, flow, xs, ys, out, C, H, W, q, qs);

@@ -536,7 +536,8 @@ def test_warp_tokens_argument_errors_and_unsupported_channels():
     assert d01 <= 1e-4 and d23 <= 1e-4, (d01, d23)
 
 
-@pytest.mark.parametrize("case", [(2, 16, 128, 128, 0.7), (1, 32, 64, 96, 3.0), (1, 128, 9, 33, 1.0), (2, 4, 31, 17, 5.0)])
+@pytest.mark.parametrize("case", [(2, 16, 128, 128, 0.7), (1, 32, 64, 96, 3.0), (1, 128, 9, 33, 1.0), (2, 4, 31, 17, 5.0),
+                                  (1, 256, 16, 24, 1.0), (1, 512, 8, 12, 2.0)])      # > 32 vectors per pixel: channel groups
 def test_warp_ndhwc_forward_kernels_agree_bit_for_bit(case, variants):
     """The default NDHWC forward (one coordinate chain per pixel, footprints passed by warp shuffles) and the plain
     per-(pixel, vector) kernel (warp_fwd_variant = 0) run the same arithmetic: identical bits."""
