@@ -1140,8 +1140,9 @@ int warp_bwd_ndhwc(const T* gout, const T* x1, const T* x2, int64_t sB, const fl
     if (!gather && (bv < 0 || bv == 4) && shuffle) {
       int R = option(OPT_NDHWC_BWD_ROWS);
       const int lshift = qs < 3 ? qs : 3;
-      // measured on B200 (benchmarks/bwd_probe.py, 4 CTAs per SM): 4-row tiles for >= 32 channels, 8-row tiles below
-      if (R <= 0) R = lshift == 3 ? 4 : 8;
+      // measured on B200 (benchmarks/bwd_probe.py, 4 CTAs per SM): 5-row tiles for >= 32 channels (0.71-0.73 of the roofline;
+      // 4 rows: 0.70-0.72, 6 rows: 0.63-0.68), 8-row tiles below
+      if (R <= 0) R = lshift == 3 ? 5 : 8;
       if (R > H) R = H;
       // next item's x taps prefetched through shared-memory slots (knob ndhwc_bwd_pf: -1 auto, 0 off, 1 on).  Measured on
       // B200 (benchmarks/bwd_probe.py): +4 % / +11 % at C = 128 / 256 (many 32-channel chunks per tile: the prefetch runs
