@@ -167,7 +167,10 @@ SMOW_API int smow_act_tlerp_cat_bwd(const void* gcat, const void* z, void* gz, v
  *      (bn is a [6][C] fp32 block); running_mean / running_var updated like nn.BatchNorm3d (momentum, unbiased variance);
  *   3. smow_bn_act_tlerp_cat_fwd: cat[:, :Cd] = leaky_relu(y*scale + shift), cat[:, Cd:] = lerped skip (Cs may be 0);
  *   backward: smow_bn_act_bwd_reduce (sum du, sum du*xhat -> bn[4], bn[5], dgamma, dbeta) then
- *   smow_bn_act_tlerp_cat_bwd (gy = scale*(du - k1 - xhat*k2) dense + the lerp's gskip).  fp32, NDHWC, deterministic. */
+ *   smow_bn_act_tlerp_cat_bwd (gy = scale*(du - k1 - xhat*k2) dense + the lerp's gskip).  fp32, NDHWC, deterministic.
+ *   The apply pass reads every gradient row with one load instruction per (pixel, frame) — decoder slice and skip slice
+ *   together — so each 128-byte line of the gradient comes from HBM once whatever the channel split (knob "bn_bwd_rows" = 0
+ *   selects the earlier kernel with separate decoder / skip CTAs; identical results).                                    */
 SMOW_API int     smow_frame_mix_stats_parts(int B, int C, int T, int64_t hw);
 SMOW_API int     smow_frame_mix_apply_tc_stats(const float* in, const float* wpack, const float* bias, float* out, float* stats,
                          int B, int C, int T, int64_t hw, int64_t out_pitch, int shift, int own_off, void* stream);
