@@ -108,3 +108,32 @@ def test_widened_operators_have_no_cpu_path_either():
         ops.frame_mix(x, torch.zeros(16, 16), torch.zeros(4, 16, 16))
     assert _lib.load().smow_frame_mix_supported(28) == 1 and _lib.load().smow_frame_mix_supported(24) == 0
     assert _lib.load().smow_tokenizer_workspace_bytes(2, 16, 16384) == 4 * 2 * 32 * (16 + 8 * 16) * 4
+
+
+def test_fused_warp_tokens_has_no_cpu_path_and_reports_argument_errors():
+    """Rows A1 + N2 fused: ops.warp_tokens refuses CPU tensors (the modules then run flow_warp + the tokenizer loop, which the
+    CPU tests route to the oracle); the C entry points report bad arguments through their return code; the support query and
+    the knob of the row-wise BatchNorm backward work without a GPU."""
+    x, flow = torch.zeros(1, 16, 2, 8, 8), torch.zeros(1, 2, 2, 8, 8)
+    w, b = torch.zeros(8, 16, 1, 1), torch.zeros(8)
+    assert not ops.warp_tokens_supported(x, w)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.warp_tokens(x, flow, w, b)
+    lib = _lib.load()
+    assert lib.smow_warp_tokenizer_supported(16) == 1 and lib.smow_warp_tokenizer_supported(32) == 1
+    assert lib.smow_warp_tokenizer_supported(64) == 0 and lib.smow_warp_tokenizer_supported(28) == 0
+    old = _lib.get_option("tok_variant")
+    _lib.set_option("tok_variant", 0)                       # the fused pass exists only in the tensor-core family
+    try:
+        assert lib.smow_warp_tokenizer_supported(16) == 0
+    finally:
+        _lib.set_option("tok_variant", old)
+    rc = lib.smow_warp_tokenizer_fwd(None, None, None, None, None, None, None, None, 1, 16, 8, 8, 0, 1, None, 0, None)
+    assert rc == -1 and lib.smow_last_error()
+    rc = lib.smow_warp_tokenizer_bwd(None, None, None, None, None, None, None, None, None, None, None, None, 1, 16, 0, 8, 0, 1,
+                                     None, 0, None)
+    assert rc == -1
+    assert _lib.get_option("bn_bwd_rows") == 1
+    _lib.set_option("bn_bwd_rows", 0)
+    assert _lib.get_option("bn_bwd_rows") == 0
+    _lib.set_option("bn_bwd_rows", 1)
