@@ -111,8 +111,7 @@ warp_fwd_ndhwc_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int64_
 // unchanged (bit-identical results); 3.5x fewer instructions at C = 32.
 // grid: x = ceil(HW / 256) (8 warps x 32 pixels), y = 2*B.
 template <typename T>
-__global__ void __launch_bounds__(256)
-warp_fwd_ndhwc_shfl_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int64_t sB,
+__device__ __forceinline__ void warp_fwd_ndhwc_shfl_body(const T* __restrict__ x1, const T* __restrict__ x2, int64_t sB,
                            const float* __restrict__ flow, const float* __restrict__ xs, const float* __restrict__ ys,
                            T* __restrict__ out, int C, int H, int W, int q, int qshift, int wshift) {
   constexpr int V = CVec<T>::N;
@@ -212,6 +211,24 @@ warp_fwd_ndhwc_shfl_kernel(const T* __restrict__ x1, const T* __restrict__ x2, i
       }
     }
   }
+}
+
+// Two launch shapes of the same body (measured on B200, benchmarks/fwd_cold_probe.py): fp32 is best left to the compiler
+// (48 registers, 5 CTAs per SM: 0.83-0.89; forcing 5 CTAs gives 46 registers and 0.77-0.84); the unrolled bf16 loop wants 4 CTAs
+// per SM (64 registers, 32 B of spills: 0.71-0.77 instead of 0.65-0.75 at 69 registers / 3 CTAs).
+template <typename T>
+__global__ void __launch_bounds__(256)
+warp_fwd_ndhwc_shfl_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int64_t sB,
+                           const float* __restrict__ flow, const float* __restrict__ xs, const float* __restrict__ ys,
+                           T* __restrict__ out, int C, int H, int W, int q, int qshift, int wshift) {
+  warp_fwd_ndhwc_shfl_body<T>(x1, x2, sB, flow, xs, ys, out, C, H, W, q, qshift, wshift);
+}
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+warp_fwd_ndhwc_shfl4_kernel(const T* __restrict__ x1, const T* __restrict__ x2, int64_t sB,
+                            const float* __restrict__ flow, const float* __restrict__ xs, const float* __restrict__ ys,
+                            T* __restrict__ out, int C, int H, int W, int q, int qshift, int wshift) {
+  warp_fwd_ndhwc_shfl_body<T>(x1, x2, sB, flow, xs, ys, out, C, H, W, q, qshift, wshift);
 }
 
 // ------------------------------------------------------------------------------
@@ -1065,7 +1082,10 @@ int warp_fwd_ndhwc(const T* x1, const T* x2, int64_t sB, const float* flow, cons
   if (qs >= 0 && q <= 2048 && option(OPT_WARP_FWD_VARIANT) != 0) {        // default: per-pixel coordinates, shuffled
     const int qg = q <= 32 ? q : 32;                                        // vectors per pixel handled by one warp pass
     dim3 grid((unsigned)(((int64_t)H * W + 255) / 256), 2 * B, q / qg);
-    warp_fwd_ndhwc_shfl_kernel<T><<<grid, 256, 0, st>>>(x1, x2, sB, flow, xs, ys, out, C, H, W, qg, ilog2_exact(qg), ilog2_exact(W));
+    if constexpr (std::is_same<T, float>::value)
+      warp_fwd_ndhwc_shfl_kernel<T><<<grid, 256, 0, st>>>(x1, x2, sB, flow, xs, ys, out, C, H, W, qg, ilog2_exact(qg), ilog2_exact(W));
+    else
+      warp_fwd_ndhwc_shfl4_kernel<T><<<grid, 256, 0, st>>>(x1, x2, sB, flow, xs, ys, out, C, H, W, qg, ilog2_exact(qg), ilog2_exact(W));
   } else {                                                                 // any q; also warp_fwd_variant = 0
     dim3 grid((unsigned)(((int64_t)H * W * q + 255) / 256), 2 * B);
     warp_fwd_ndhwc_kernel<T><<<grid, 256, 0, st>>>(x1, x2, sB, flow, xs, ys, out, C, H, W, q, qs);
